@@ -1,0 +1,458 @@
+// C ABI of libbunmpc.so (include/bunmpc.h): solver handle, staging buffers, kernel dispatch.
+// Host orchestration only; the arithmetic is in kernels.cuh.  No CPU fallback anywhere: if a CUDA call
+// fails the entry point returns BUNMPC_ERR_CUDA and bunmpc_last_error() says why.
+#include "../../include/bunmpc.h"
+#include "kernels.cuh"
+#include "tables.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bunmpc;
+
+static thread_local std::string g_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return BUNMPC_ERR_CUDA;                                                                \
+        }                                                                                          \
+    } while (0)
+
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+struct DevTables {
+    TablesDev d{};
+    std::vector<void *> allocs;
+};
+
+struct bunmpc_solver {
+    int device = 0, n = 0, e = 0, nx = 0, nf = 0, max_batch = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    DevTables TF, TX;
+    unsigned int *work_counter = nullptr;
+    double *coef = nullptr;          // device, [coef_len]
+    int coef_len = 0;
+    // staging (device), sized for max_batch
+    double *st_in = nullptr;         // compact / expanded inputs copied from the host
+    size_t st_in_doubles = 0;
+    double *ex = nullptr;            // expanded Qx,qx,lbx,ubx,Qf,qf
+    double *out_d = nullptr;         // X,F,P,L,viol,(hist)
+    int *out_i = nullptr;            // iters, status
+    double *mats = nullptr;          // scratch for bunmpc_centroidal_mats_host
+    long long launches = 0;
+    int nthreads = 0, smem_bytes = 0, nav = 0;
+    int ctas_per_sm[2] = {0, 0};     // per arith
+};
+
+template <class T>
+static cudaError_t upload(DevTables &D, const std::vector<T> &h, const T **dst)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, h.size() * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    D.allocs.push_back(p);
+    *dst = reinterpret_cast<const T *>(p);
+    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static cudaError_t upload_tables(DevTables &D, const HostTables &H)
+{
+    cudaError_t e;
+    D.d.nv = H.nv; D.d.nr = H.nr; D.d.nvp = H.nvp; D.d.nrp = H.nrp;
+    if ((e = upload(D, H.h_len, &D.d.h_len)) != cudaSuccess) return e;
+    if ((e = upload(D, H.h_np, &D.d.h_np)) != cudaSuccess) return e;
+    if ((e = upload(D, H.c_len, &D.d.c_len)) != cudaSuccess) return e;
+    if ((e = upload(D, H.a_len, &D.d.a_len)) != cudaSuccess) return e;
+    if ((e = upload(D, H.h_col, &D.d.h_col)) != cudaSuccess) return e;
+    if ((e = upload(D, H.c_row, &D.d.c_row)) != cudaSuccess) return e;
+    if ((e = upload(D, H.c_aidx, &D.d.c_aidx)) != cudaSuccess) return e;
+    if ((e = upload(D, H.a_col, &D.d.a_col)) != cudaSuccess) return e;
+    if ((e = upload(D, H.a_aidx, &D.d.a_aidx)) != cudaSuccess) return e;
+    if ((e = upload(D, H.h_pair, &D.d.h_pair)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+// ---- kernel dispatch: thread-count classes with their own register budgets ----
+typedef void (*solve_fn)(const SolveArgs);
+
+template <int NE, int ARITH>
+static solve_fn pick_kernel(int nthreads)
+{
+    if (nthreads <= 256) return solve_kernel<NE, ARITH, 256, 2>;
+    if (nthreads <= 384) return solve_kernel<NE, ARITH, 384, 1>;
+    if (nthreads <= 512) return solve_kernel<NE, ARITH, 512, 1>;
+    if (nthreads <= 768) return solve_kernel<NE, ARITH, 768, 1>;
+    return solve_kernel<NE, ARITH, 1024, 1>;
+}
+
+static solve_fn pick(int e, int arith, int nthreads)
+{
+    if (e == 4) return arith ? pick_kernel<4, 1>(nthreads) : pick_kernel<4, 0>(nthreads);
+    return nullptr;
+}
+
+static size_t smem_doubles(int n, int e, int max_inner, int nav)
+{
+    int nx = 9 * (n + 1), nf = 3 * e * n, nm = nx > nf ? nx : nf;
+    return (size_t)nx * 4 + nf + 2 * (size_t)nm + nav + 4 * (size_t)e * n + n + max_inner + 8 * 32 + 4 + 2;
+}
+
+extern "C" {
+
+int bunmpc_version(void) { return BUNMPC_VERSION; }
+const char *bunmpc_last_error(void) { return g_err.c_str(); }
+
+void bunmpc_default_params(bunmpc_params *p)
+{
+    p->max_outer = 100; p->max_inner = 150; p->tol = 1e-5; p->exit_tol = 1e-3; p->beta = 1.5; p->mu = 1.0;
+    p->arith = BUNMPC_ARITH_STRICT;
+}
+
+void *bunmpc_host_alloc(unsigned long long bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void bunmpc_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+static const int kMaxInnerTable = 4096;
+
+int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max_batch)
+{
+    if (!out || n_col < 1 || max_batch < 1) return fail(BUNMPC_ERR_ARG, "bunmpc_create: bad argument");
+    if (n_eff != 4) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: kernels are built for n_eff == 4");
+    const int n = n_col, e = n_eff, nx = 9 * (n + 1), nf = 3 * e * n;
+    const int wf = (nf + 29) / 30, wx = (nx + 31) / 32;
+    const int nthreads = 32 * (wf > wx ? wf : wx);
+    if (nthreads > 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: n_col too large for one CTA per instance");
+    CK(cudaSetDevice(device));
+    bunmpc_solver *s = new bunmpc_solver();
+    s->device = device; s->n = n; s->e = e; s->nx = nx; s->nf = nf; s->max_batch = max_batch;
+    s->nthreads = nthreads;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    s->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+
+    // symbolic tables
+    HostTables hf = build_tables(pattern_Ax(n, e), nx, nf, 9 * e * n, 3 * e, 3, 2 * e, 3);
+    HostTables hx = build_tables(pattern_Af(n), nx, nx, 27 * n + 9, 11, 4, 4, 4);
+    if (hf.KH > 3 * e || hf.PM > 3 || hf.KA > 2 * e || hf.KC > 3 || hx.KH > 11 || hx.PM > 4 || hx.KA > 4 || hx.KC > 4) {
+        delete s;
+        return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: sparsity pattern exceeds the kernel's table bounds");
+    }
+    CK(upload_tables(s->TF, hf));
+    CK(upload_tables(s->TX, hx));
+    s->nav = (9 * e * n > 27 * n + 9) ? 9 * e * n : 27 * n + 9;
+
+    // FISTA momentum coefficients (t_k - 1)/t_{k+1} with t_{k+1} = 1 + sqrt(1 + 4 t_k^2)/2 (fista.cpp:34-35, sic);
+    // the sequence does not depend on the data, so it is tabulated once (IEEE sqrt and / are exact on both sides).
+    {
+        std::vector<double> c(kMaxInnerTable);
+        volatile double t_k = 1.0;
+        for (int i = 0; i < kMaxInnerTable; ++i) {
+            volatile double sq = 4 * t_k * t_k;
+            volatile double t_k_1 = 1.0 + std::sqrt(1 + sq) / 2.0;
+            c[i] = (t_k - 1) / t_k_1;
+            t_k = t_k_1;
+        }
+        CK(cudaMalloc(&s->coef, sizeof(double) * kMaxInnerTable));
+        CK(cudaMemcpy(s->coef, c.data(), sizeof(double) * kMaxInnerTable, cudaMemcpyHostToDevice));
+        s->coef_len = kMaxInnerTable;
+    }
+    CK(cudaMalloc(&s->work_counter, sizeof(unsigned int)));
+
+    // staging buffers
+    const size_t B = (size_t)max_batch;
+    const size_t in_doubles = B * (2 + 9 + 4 * (size_t)e * n + n + 2 + 2 * (size_t)nx + nf     // m,rho,x_init,cnt,dt,L0,X0,P0,F0
+                                   + 4 * (size_t)nx + 2 * (size_t)nf + 6 * (size_t)n + 18) + 64;  // costs/bounds in either form
+    s->st_in_doubles = in_doubles;
+    CK(cudaMalloc(&s->st_in, sizeof(double) * in_doubles));
+    CK(cudaMalloc(&s->ex, sizeof(double) * B * (4 * (size_t)nx + 2 * (size_t)nf)));
+    CK(cudaMalloc(&s->out_d, sizeof(double) * B * (2 * (size_t)nx + nf + 3)));
+    CK(cudaMalloc(&s->out_i, sizeof(int) * B * 6));
+    CK(cudaMalloc(&s->mats, sizeof(double) * ((size_t)nx * nf + (size_t)nx * nx + 2 * (size_t)nx + 4 * (size_t)e * n + n + nx + nf + 9)));
+
+    // opt in to the shared memory the kernel needs and record occupancy
+    s->smem_bytes = (int)(smem_doubles(n, e, 150, s->nav) * sizeof(double));
+    for (int arith = 0; arith < 2; ++arith) {
+        solve_fn fn = pick(e, arith, nthreads);
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, nthreads, s->smem_bytes));
+        s->ctas_per_sm[arith] = nb;
+    }
+    *out = s;
+    return BUNMPC_OK;
+}
+
+void bunmpc_destroy(bunmpc_solver *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (void *p : s->TF.allocs) cudaFree(p);
+    for (void *p : s->TX.allocs) cudaFree(p);
+    cudaFree(s->work_counter); cudaFree(s->coef); cudaFree(s->st_in); cudaFree(s->ex);
+    cudaFree(s->out_d); cudaFree(s->out_i); cudaFree(s->mats);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+long long bunmpc_launch_count(const bunmpc_solver *s) { return s ? s->launches : 0; }
+
+int bunmpc_kernel_info(const bunmpc_solver *s, int *ctas_per_sm, int *threads, int *smem_bytes, int *num_sms)
+{
+    if (!s) return fail(BUNMPC_ERR_ARG, "null solver");
+    if (ctas_per_sm) *ctas_per_sm = s->ctas_per_sm[0];
+    if (threads) *threads = s->nthreads;
+    if (smem_bytes) *smem_bytes = s->smem_bytes;
+    if (num_sms) *num_sms = s->num_sms;
+    return BUNMPC_OK;
+}
+
+static In mk(const bunmpc_in &f) { return In{f.ptr, f.batch_stride}; }
+
+static int check_params(const bunmpc_solver *s, const bunmpc_params *prm)
+{
+    if (!prm) return fail(BUNMPC_ERR_ARG, "null params");
+    if (prm->max_outer < 0 || prm->max_inner < 1 || prm->max_inner > s->coef_len)
+        return fail(BUNMPC_ERR_ARG, "max_inner/max_outer out of range");
+    if (prm->arith != BUNMPC_ARITH_STRICT && prm->arith != BUNMPC_ARITH_FMA)
+        return fail(BUNMPC_ERR_UNSUPPORTED, "unknown arith mode");
+    return BUNMPC_OK;
+}
+
+int bunmpc_expand_device(bunmpc_solver *s, const bunmpc_compact_problem *p, double *Qx, double *qx, double *Qf,
+                         double *qf, double *lbx, double *ubx, void *stream)
+{
+    if (!s || !p || !Qx || !qx || !Qf || !qf || !lbx || !ubx) return fail(BUNMPC_ERR_ARG, "expand: null argument");
+    if (p->batch < 1) return fail(BUNMPC_ERR_ARG, "expand: batch < 1");
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    ExpandArgs a;
+    a.B = p->batch; a.n = s->n; a.e = s->e; a.nx = s->nx; a.nf = s->nf;
+    a.cnt_plan = mk(p->cnt_plan); a.W_X = mk(p->W_X); a.W_X_ter = mk(p->W_X_ter); a.X_nom = mk(p->X_nom);
+    a.X_ter = mk(p->X_ter); a.W_F = mk(p->W_F); a.bounds = mk(p->bounds);
+    a.Qx = Qx; a.qx = qx; a.Qf = Qf; a.qf = qf; a.lbx = lbx; a.ubx = ubx;
+    const long long total = (long long)a.B * (a.nx > a.nf ? a.nx : a.nf);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)s->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    expand_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    s->launches++;
+    CK(cudaGetLastError());
+    return BUNMPC_OK;
+}
+
+int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem *p, const bunmpc_params *prm,
+                                 const bunmpc_solution *out, void *stream)
+{
+    if (!s || !p || !out) return fail(BUNMPC_ERR_ARG, "solve: null argument");
+    int rc = check_params(s, prm);
+    if (rc) return rc;
+    if (p->batch < 1) return fail(BUNMPC_ERR_ARG, "solve: batch < 1");
+    if (!p->m.ptr || !p->rho.ptr || !p->x_init.ptr || !p->cnt_plan.ptr || !p->dt.ptr || !p->Qx.ptr || !p->qx.ptr ||
+        !p->Qf.ptr || !p->qf.ptr || !p->lbx.ptr || !p->ubx.ptr || !p->L0.ptr)
+        return fail(BUNMPC_ERR_ARG, "solve: null input field");
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    SolveArgs a;
+    a.B = p->batch; a.n = s->n; a.e = s->e; a.nx = s->nx; a.nf = s->nf;
+    a.m = mk(p->m); a.rho = mk(p->rho); a.x_init = mk(p->x_init); a.cnt_plan = mk(p->cnt_plan); a.dt = mk(p->dt);
+    a.Qx = mk(p->Qx); a.qx = mk(p->qx); a.Qf = mk(p->Qf); a.qf = mk(p->qf); a.lbx = mk(p->lbx); a.ubx = mk(p->ubx);
+    a.L0 = mk(p->L0); a.X0 = mk(p->X0); a.F0 = mk(p->F0); a.P0 = mk(p->P0);
+    a.X = out->X; a.F = out->F; a.P = out->P; a.L = out->L; a.viol = out->viol; a.viol_hist = out->viol_hist;
+    a.iters = out->iters; a.status = out->status;
+    a.max_outer = prm->max_outer; a.max_inner = prm->max_inner;
+    a.tol = prm->tol; a.exit_tol = prm->exit_tol; a.beta = prm->beta; a.mu = prm->mu;
+    a.coef = s->coef; a.TF = s->TF.d; a.TX = s->TX.d; a.work_counter = s->work_counter; a.nav = s->nav;
+    const int smem = (int)(smem_doubles(s->n, s->e, prm->max_inner, s->nav) * sizeof(double));
+    if (smem > 200 * 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: shared memory need exceeds 200 KB");
+    solve_fn fn = pick(s->e, prm->arith, s->nthreads);
+    int per_sm = s->ctas_per_sm[prm->arith];
+    if (smem != s->smem_bytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->nthreads, smem));
+    if (per_sm < 1) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: kernel does not fit on an SM");
+    long long grid = (long long)s->num_sms * per_sm;
+    if (grid > a.B) grid = a.B;
+    CK(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), st));
+    fn<<<(unsigned)grid, s->nthreads, smem, st>>>(a);
+    s->launches++;
+    CK(cudaGetLastError());
+    return BUNMPC_OK;
+}
+
+int bunmpc_solve_compact_device(bunmpc_solver *s, const bunmpc_compact_problem *p, const bunmpc_params *prm,
+                                const bunmpc_solution *out, void *stream)
+{
+    if (!s || !p || !out) return fail(BUNMPC_ERR_ARG, "solve: null argument");
+    if (p->batch < 1 || p->batch > s->max_batch) return fail(BUNMPC_ERR_ARG, "solve: batch outside [1, max_batch]");
+    const size_t B = (size_t)p->batch, nx = (size_t)s->nx, nf = (size_t)s->nf;
+    double *Qx = s->ex, *qx = Qx + B * nx, *lbx = qx + B * nx, *ubx = lbx + B * nx, *Qf = ubx + B * nx, *qf = Qf + B * nf;
+    int rc = bunmpc_expand_device(s, p, Qx, qx, Qf, qf, lbx, ubx, stream);
+    if (rc) return rc;
+    bunmpc_expanded_problem q;
+    q.batch = p->batch;
+    q.m = p->m; q.rho = p->rho; q.x_init = p->x_init; q.cnt_plan = p->cnt_plan; q.dt = p->dt;
+    q.Qx = {Qx, (long long)nx}; q.qx = {qx, (long long)nx}; q.Qf = {Qf, (long long)nf}; q.qf = {qf, (long long)nf};
+    q.lbx = {lbx, (long long)nx}; q.ubx = {ubx, (long long)nx};
+    q.L0 = p->L0; q.X0 = p->X0; q.F0 = p->F0; q.P0 = p->P0;
+    return bunmpc_solve_expanded_device(s, &q, prm, out, stream);
+}
+
+// ---- host-pointer path: stage fields into st_in, run, copy results back ----
+struct Stager {
+    bunmpc_solver *s;
+    double *cur;
+    int B;
+    cudaError_t err = cudaSuccess;
+    bunmpc_in put(const bunmpc_in &h, size_t width)
+    {
+        bunmpc_in d{nullptr, 0};
+        if (!h.ptr || err != cudaSuccess) return d;
+        d.ptr = cur;
+        if (h.batch_stride == 0 || B == 1) {
+            err = cudaMemcpyAsync(cur, h.ptr, width * sizeof(double), cudaMemcpyHostToDevice, s->stream);
+            d.batch_stride = 0;
+            cur += width;
+        } else if ((size_t)h.batch_stride == width) {
+            err = cudaMemcpyAsync(cur, h.ptr, (size_t)B * width * sizeof(double), cudaMemcpyHostToDevice, s->stream);
+            d.batch_stride = (long long)width;
+            cur += (size_t)B * width;
+        } else {
+            err = cudaMemcpy2DAsync(cur, width * sizeof(double), h.ptr, (size_t)h.batch_stride * sizeof(double),
+                                    width * sizeof(double), (size_t)B, cudaMemcpyHostToDevice, s->stream);
+            d.batch_stride = (long long)width;
+            cur += (size_t)B * width;
+        }
+        cur += (size_t)(cur - s->st_in) & 1;   // keep 16-byte alignment
+        return d;
+    }
+};
+
+static int copy_out(bunmpc_solver *s, int B, const bunmpc_solution &dev, const bunmpc_solution *out, int max_outer)
+{
+    const size_t nx = (size_t)s->nx, nf = (size_t)s->nf, Bs = (size_t)B;
+    if (out->X) CK(cudaMemcpyAsync(out->X, dev.X, Bs * nx * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (out->F) CK(cudaMemcpyAsync(out->F, dev.F, Bs * nf * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (out->P) CK(cudaMemcpyAsync(out->P, dev.P, Bs * nx * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (out->L) CK(cudaMemcpyAsync(out->L, dev.L, Bs * 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (out->viol) CK(cudaMemcpyAsync(out->viol, dev.viol, Bs * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (out->iters) CK(cudaMemcpyAsync(out->iters, dev.iters, Bs * 5 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (out->status) CK(cudaMemcpyAsync(out->status, dev.status, Bs * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (out->viol_hist)
+        CK(cudaMemcpyAsync(out->viol_hist, dev.viol_hist, Bs * (size_t)max_outer * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return BUNMPC_OK;
+}
+
+static int dev_solution(bunmpc_solver *s, int B, const bunmpc_solution *want, int max_outer, bunmpc_solution *dev,
+                        double **hist_alloc)
+{
+    const size_t nx = (size_t)s->nx, nf = (size_t)s->nf, Bs = (size_t)B;
+    dev->X = s->out_d; dev->F = dev->X + Bs * nx; dev->P = dev->F + Bs * nf; dev->L = dev->P + Bs * nx;
+    dev->viol = dev->L + 2 * Bs;
+    dev->iters = s->out_i; dev->status = s->out_i + 5 * Bs;
+    dev->viol_hist = nullptr;
+    *hist_alloc = nullptr;
+    if (want->viol_hist) {
+        CK(cudaMalloc(hist_alloc, Bs * (size_t)max_outer * sizeof(double)));
+        dev->viol_hist = *hist_alloc;
+    }
+    return BUNMPC_OK;
+}
+
+int bunmpc_solve_compact_host(bunmpc_solver *s, const bunmpc_compact_problem *p, const bunmpc_params *prm,
+                              const bunmpc_solution *out)
+{
+    if (!s || !p || !out) return fail(BUNMPC_ERR_ARG, "solve: null argument");
+    int rc = check_params(s, prm);
+    if (rc) return rc;
+    if (p->batch < 1 || p->batch > s->max_batch) return fail(BUNMPC_ERR_ARG, "solve: batch outside [1, max_batch]");
+    CK(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->n, e = (size_t)s->e, nx = (size_t)s->nx, nf = (size_t)s->nf;
+    Stager st{s, s->st_in, p->batch};
+    bunmpc_compact_problem d;
+    d.batch = p->batch;
+    d.m = st.put(p->m, 1); d.rho = st.put(p->rho, 1); d.x_init = st.put(p->x_init, 9);
+    d.cnt_plan = st.put(p->cnt_plan, 4 * e * n); d.dt = st.put(p->dt, n);
+    d.W_X = st.put(p->W_X, 9 * n); d.W_X_ter = st.put(p->W_X_ter, 9); d.X_nom = st.put(p->X_nom, 9 * n);
+    d.X_ter = st.put(p->X_ter, 9); d.W_F = st.put(p->W_F, nf); d.bounds = st.put(p->bounds, 6 * n);
+    d.L0 = st.put(p->L0, 2); d.X0 = st.put(p->X0, nx); d.F0 = st.put(p->F0, nf); d.P0 = st.put(p->P0, nx);
+    CK(st.err);
+    bunmpc_solution dev;
+    double *hist = nullptr;
+    rc = dev_solution(s, p->batch, out, prm->max_outer, &dev, &hist);
+    if (rc) return rc;
+    rc = bunmpc_solve_compact_device(s, &d, prm, &dev, s->stream);
+    if (!rc) rc = copy_out(s, p->batch, dev, out, prm->max_outer);
+    if (hist) cudaFree(hist);
+    return rc;
+}
+
+int bunmpc_solve_expanded_host(bunmpc_solver *s, const bunmpc_expanded_problem *p, const bunmpc_params *prm,
+                               const bunmpc_solution *out)
+{
+    if (!s || !p || !out) return fail(BUNMPC_ERR_ARG, "solve: null argument");
+    int rc = check_params(s, prm);
+    if (rc) return rc;
+    if (p->batch < 1 || p->batch > s->max_batch) return fail(BUNMPC_ERR_ARG, "solve: batch outside [1, max_batch]");
+    CK(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->n, e = (size_t)s->e, nx = (size_t)s->nx, nf = (size_t)s->nf;
+    Stager st{s, s->st_in, p->batch};
+    bunmpc_expanded_problem d;
+    d.batch = p->batch;
+    d.m = st.put(p->m, 1); d.rho = st.put(p->rho, 1); d.x_init = st.put(p->x_init, 9);
+    d.cnt_plan = st.put(p->cnt_plan, 4 * e * n); d.dt = st.put(p->dt, n);
+    d.Qx = st.put(p->Qx, nx); d.qx = st.put(p->qx, nx); d.Qf = st.put(p->Qf, nf); d.qf = st.put(p->qf, nf);
+    d.lbx = st.put(p->lbx, nx); d.ubx = st.put(p->ubx, nx);
+    d.L0 = st.put(p->L0, 2); d.X0 = st.put(p->X0, nx); d.F0 = st.put(p->F0, nf); d.P0 = st.put(p->P0, nx);
+    CK(st.err);
+    bunmpc_solution dev;
+    double *hist = nullptr;
+    rc = dev_solution(s, p->batch, out, prm->max_outer, &dev, &hist);
+    if (rc) return rc;
+    rc = bunmpc_solve_expanded_device(s, &d, prm, &dev, s->stream);
+    if (!rc) rc = copy_out(s, p->batch, dev, out, prm->max_outer);
+    if (hist) cudaFree(hist);
+    return rc;
+}
+
+int bunmpc_centroidal_mats_host(bunmpc_solver *s, double m, const double *cnt_plan, const double *dt, const double *X,
+                                const double *F, const double *x_init, double *A_x, double *b_x, double *A_f,
+                                double *b_f)
+{
+    if (!s || !cnt_plan || !dt) return fail(BUNMPC_ERR_ARG, "mats: null argument");
+    if ((A_x || b_x) && !X) return fail(BUNMPC_ERR_ARG, "mats: X required for A_x/b_x");
+    if ((A_f || b_f) && (!F || !x_init)) return fail(BUNMPC_ERR_ARG, "mats: F and x_init required for A_f/b_f");
+    CK(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->n, e = (size_t)s->e, nx = (size_t)s->nx, nf = (size_t)s->nf;
+    double *dAx = s->mats, *dAf = dAx + nx * nf, *dbx = dAf + nx * nx, *dbf = dbx + nx;
+    double *dcnt = dbf + nx, *ddt = dcnt + 4 * e * n, *dX = ddt + n, *dF = dX + nx, *dxi = dF + nf;
+    cudaStream_t st = s->stream;
+    CK(cudaMemcpyAsync(dcnt, cnt_plan, 4 * e * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ddt, dt, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (X) CK(cudaMemcpyAsync(dX, X, nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (F) CK(cudaMemcpyAsync(dF, F, nf * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (x_init) CK(cudaMemcpyAsync(dxi, x_init, 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dAx, 0, (nx * nf + nx * nx) * sizeof(double), st));
+    dense_mats_kernel<4><<<4, 128, 0, st>>>((int)n, m, dcnt, ddt, X ? dX : nullptr, F ? dF : nullptr, dxi,
+                                            (A_x ? dAx : nullptr), (b_x ? dbx : nullptr), (A_f ? dAf : nullptr),
+                                            (b_f ? dbf : nullptr));
+    s->launches++;
+    CK(cudaGetLastError());
+    if (A_x) CK(cudaMemcpyAsync(A_x, dAx, nx * nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (b_x) CK(cudaMemcpyAsync(b_x, dbx, nx * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (A_f) CK(cudaMemcpyAsync(A_f, dAf, nx * nx * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (b_f) CK(cudaMemcpyAsync(b_f, dbf, nx * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BUNMPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+/*
+ * bunmpc.h -- C ABI of the B200-native batched BiConMP centroidal biconvex solver.
+ *
+ * This is the drop-in boundary for ONE path of Atarilab/BUNMPC: BiConvexMP::optimize and what it
+ * calls.  It replaces the pybind11 module `biconvex_mpc_cpp`
+ * (iterative_supervised_learning/srcpy/motion_planner/biconvex.cpp:15-44) for that path: every entry
+ * point below names the reference interface it stands in for.  Plain pointers and sizes only; no
+ * C++/torch types.  All floating-point data is IEEE binary64 ("f64"), C-contiguous.
+ *
+ * Shapes:  n = n_col, e = n_eff, nx = 9 (n + 1), nf = 3 e n, B = batch.
+ * A `bunmpc_in` with batch_stride 0 is shared by all instances of the batch.
+ *
+ * There is no CPU fallback: every solve runs the sm_100a kernels in libbunmpc.so.
+ */
+#ifndef BUNMPC_H
+#define BUNMPC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BUNMPC_VERSION 100
+
+enum {
+    BUNMPC_OK = 0,
+    BUNMPC_ERR_ARG = 1,          /* bad argument (null pointer, batch > max_batch, ...) */
+    BUNMPC_ERR_UNSUPPORTED = 2,  /* n_col / n_eff / option outside what the kernels are built for */
+    BUNMPC_ERR_CUDA = 3          /* CUDA runtime error, see bunmpc_last_error() */
+};
+
+/* per-instance exit status (biconvex.cpp:106-114) */
+enum { BUNMPC_CONVERGED = 0, BUNMPC_MAX_ITERS = 1, BUNMPC_NAN = 2 };
+
+/* arithmetic variants; BUNMPC_ARITH_STRICT reproduces the oracle's unfused operation order bit for bit,
+ * BUNMPC_ARITH_FMA fuses the multiply-adds of the mat-vecs (oracle: use_fma = 1). */
+enum { BUNMPC_ARITH_STRICT = 0, BUNMPC_ARITH_FMA = 1 };
+
+typedef struct bunmpc_solver bunmpc_solver;   /* opaque: device, stream, tables, staging buffers */
+
+/* Solver constants.  Defaults = the reference's member initialisers, none of which python can change
+ * (biconvex.hpp:148-160, fista.hpp:52-60; num_iters is the argument of BiConvexMP::optimize). */
+typedef struct {
+    int    max_outer;   /* 100 (cyclic gaits) / 50 (acyclic) */
+    int    max_inner;   /* 150 */
+    double tol;         /* 1e-5 */
+    double exit_tol;    /* 1e-3 */
+    double beta;        /* 1.5 */
+    double mu;          /* 1.0 */
+    int    arith;       /* BUNMPC_ARITH_* */
+} bunmpc_params;
+
+typedef struct {
+    const double *ptr;
+    long long     batch_stride;   /* in elements; 0 = one copy shared by the whole batch */
+} bunmpc_in;
+
+/* What the gait generator hands to one BiconvexMP object per solve, batched
+ * (abstract_cyclic_gen.py:391,611-614,663). */
+typedef struct {
+    int batch;
+    bunmpc_in m;          /* [B]            ctor argument m            biconvex.cpp:6 */
+    bunmpc_in rho;        /* [B]            set_rho                    biconvex.hpp:62-64 */
+    bunmpc_in x_init;     /* [B][9]         optimize(x_init, .)        biconvex.cpp:80-82 */
+    bunmpc_in cnt_plan;   /* [B][n][e][4]   set_contact_plan rows (c,x,y,z)  centroidal.cpp:39-49 */
+    bunmpc_in dt;         /* [B][n]         set_contact_plan dt */
+    bunmpc_in W_X;        /* [B][9n]        create_cost_X              biconvex.cpp:60-72 */
+    bunmpc_in W_X_ter;    /* [B][9] */
+    bunmpc_in X_nom;      /* [B][9n] */
+    bunmpc_in X_ter;      /* [B][9] */
+    bunmpc_in W_F;        /* [B][nf]        create_cost_F              biconvex.cpp:74-78 */
+    bunmpc_in bounds;     /* [B][n][6]      create_bound_constraints   biconvex.cpp:27-58 */
+    bunmpc_in L0;         /* [B][2]         FISTA step state (L_f, L_x); fresh object (506.25, 2.25e6)  biconvex.cpp:20-21 */
+    bunmpc_in X0, F0, P0; /* [B][nx],[B][nf],[B][nx]  set_warm_start_vars (biconvex.hpp:66-70);
+                             ptr == NULL selects the cold start of kino_dyn.cpp:83-99: X = tile(x_init), F = 0, P = 0 */
+} bunmpc_compact_problem;
+
+/* Same, with costs and bounds already expanded (set_cost_x / set_cost_f / set_bounds_x with diagonal Q,
+ * biconvex.hpp:54-60,72-73). */
+typedef struct {
+    int batch;
+    bunmpc_in m, rho, x_init, cnt_plan, dt;
+    bunmpc_in Qx, qx;     /* [B][nx] diagonal of Q_x, q_x */
+    bunmpc_in Qf, qf;     /* [B][nf] */
+    bunmpc_in lbx, ubx;   /* [B][nx] */
+    bunmpc_in L0;
+    bunmpc_in X0, F0, P0; /* all three required here */
+} bunmpc_expanded_problem;
+
+/* Results, contiguous with leading batch dimension.  Any pointer may be NULL (not written). */
+typedef struct {
+    double *X;          /* [B][nx]  return_opt_x   biconvex.hpp:112-114 */
+    double *F;          /* [B][nf]  return_opt_f   biconvex.hpp:116-118 */
+    double *P;          /* [B][nx]  return_opt_p   biconvex.hpp:120-122 */
+    double *L;          /* [B][2]   (L_f, L_x) after the solve: the state a FISTA object carries to its next call */
+    int    *iters;      /* [B][5]   outer, sum inner F, sum inner X, line-search rejections F, X */
+    double *viol;       /* [B]      ||A_f X - b_f|| of the last outer iteration */
+    int    *status;     /* [B]      BUNMPC_CONVERGED / MAX_ITERS / NAN */
+    double *viol_hist;  /* [B][max_outer] return_dyn_viol_hist (collect_statistics), NaN-padded */
+} bunmpc_solution;
+
+int         bunmpc_version(void);
+const char *bunmpc_last_error(void);
+void        bunmpc_default_params(bunmpc_params *p);
+
+/* BiConvexMP::BiConvexMP(m, n_col, n_eff) (biconvex.cpp:6-25): allocates everything a batch of up to
+ * max_batch instances needs on `device` (tables, staging buffers, a stream).  No allocation afterwards. */
+int  bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max_batch);
+void bunmpc_destroy(bunmpc_solver *s);
+
+/* kernel launches issued by this solver since creation (for bench.py's gpu_launches) */
+long long bunmpc_launch_count(const bunmpc_solver *s);
+/* CUDA occupancy of the solve kernel for this solver: CTAs per SM, threads per CTA, dynamic smem bytes */
+int  bunmpc_kernel_info(const bunmpc_solver *s, int *ctas_per_sm, int *threads, int *smem_bytes, int *num_sms);
+
+/* ---- device-pointer entry points: asynchronous on `stream` (a cudaStream_t; NULL = the solver's own).
+ *      All pointers in the structs are device pointers on the solver's device. ---- */
+
+/* create_bound_constraints + create_cost_X + create_cost_F for a batch (biconvex.cpp:27-78):
+ * writes Qx,qx,lbx,ubx [B][nx] and Qf,qf [B][nf]. */
+int bunmpc_expand_device(bunmpc_solver *s, const bunmpc_compact_problem *p,
+                         double *Qx, double *qx, double *Qf, double *qf, double *lbx, double *ubx, void *stream);
+/* BiConvexMP::optimize on expanded inputs (biconvex.cpp:80-120). */
+int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem *p, const bunmpc_params *prm,
+                                 const bunmpc_solution *out, void *stream);
+/* create_* followed by optimize: the whole per-solve protocol of abstract_cyclic_gen.py:391,611-614,663. */
+int bunmpc_solve_compact_device(bunmpc_solver *s, const bunmpc_compact_problem *p, const bunmpc_params *prm,
+                                const bunmpc_solution *out, void *stream);
+
+/* ---- host-pointer entry points: copy in, solve, copy out, synchronise.  Pointers are host pointers
+ *      (pinned memory makes the copies asynchronous).  This is what the python BiconvexMP calls. ---- */
+int bunmpc_solve_compact_host(bunmpc_solver *s, const bunmpc_compact_problem *p, const bunmpc_params *prm,
+                              const bunmpc_solution *out);
+int bunmpc_solve_expanded_host(bunmpc_solver *s, const bunmpc_expanded_problem *p, const bunmpc_params *prm,
+                               const bunmpc_solution *out);
+
+/* return_A_x / return_b_x / return_A_f / return_b_f (biconvex.hpp:30-51) for ONE instance, dense row-major,
+ * host pointers: A_x [nx][nf], b_x [nx], A_f [nx][nx], b_f [nx].  Any output may be NULL. */
+int bunmpc_centroidal_mats_host(bunmpc_solver *s, double m, const double *cnt_plan, const double *dt,
+                                const double *X, const double *F, const double *x_init,
+                                double *A_x, double *b_x, double *A_f, double *b_f);
+
+/* pinned host memory helpers for callers without a CUDA runtime of their own */
+void *bunmpc_host_alloc(unsigned long long bytes);
+void  bunmpc_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,55 @@
+"""GPU parity tests proper: the CUDA path through the C ABI against the CPU oracle, bit for bit
+(integer counters and IEEE binary64 values identical), on the same seeded inputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _require_gpu():
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+
+
+def assert_same(sol, ref, what=""):
+    assert np.array_equal(sol.iters, ref["iters"]), f"{what}: iteration counters differ\n{sol.iters}\n{ref['iters']}"
+    assert np.array_equal(sol.status, ref["status"]), f"{what}: status differs"
+    for k in ("F", "X", "P", "L", "viol"):
+        a, b = getattr(sol, k), ref[k]
+        same = (a == b) | (np.isnan(a) & np.isnan(b))
+        assert same.all(), f"{what}: {k} differs in {np.count_nonzero(~same)} entries, max abs {np.nanmax(np.abs(a - b))}"
+
+
+def test_nominal_single_solve(oracle):
+    """BASELINE config 1: Solo12 trot, one solve."""
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.nominal()
+    s = BatchSolver(b.n_col, b.n_eff, max_batch=1)
+    sol = s.solve(b)
+    ref = oracle.solve(b)
+    assert_same(sol, ref, "nominal")
+    assert sol.status[0] == 0 and sol.viol[0] < 1e-3
+    assert s.launch_count() == 2          # expand + solve
+
+
+@pytest.mark.parametrize("gait,B,seed", [("trot", 64, 0), ("bound", 16, 1), ("jump", 16, 2)])
+def test_perturbed_batches(oracle, gait, B, seed):
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.perturbed(B, "solo12", gait, seed=seed)
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=B).solve(b)
+    ref = oracle.solve(b, n_threads=8)
+    assert_same(sol, ref, gait)
+
+
+def test_fma_mode_matches_fma_oracle(oracle):
+    _require_gpu()
+    from bunmpc_b200 import synthetic, ARITH_FMA
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.perturbed(32, "solo12", "trot", seed=5)
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=32).solve(b, arith=ARITH_FMA)
+    ref = oracle.solve(b, params=oracle.default_params(use_fma=1), n_threads=8)
+    assert_same(sol, ref, "fma")
