@@ -51,7 +51,7 @@ class Solution(C.Structure):
 EXPORTS = ("bunmpc_version", "bunmpc_last_error", "bunmpc_default_params", "bunmpc_create", "bunmpc_destroy",
            "bunmpc_launch_count", "bunmpc_kernel_info", "bunmpc_expand_device", "bunmpc_solve_expanded_device",
            "bunmpc_solve_compact_device", "bunmpc_solve_compact_host", "bunmpc_solve_expanded_host",
-           "bunmpc_centroidal_mats_host", "bunmpc_host_alloc", "bunmpc_host_free")
+           "bunmpc_centroidal_mats_host", "bunmpc_measure_fp64_peak", "bunmpc_selftest_division", "bunmpc_host_alloc", "bunmpc_host_free")
 
 _lib = None
 
@@ -88,6 +88,8 @@ def lib():
     L.bunmpc_solve_expanded_host.argtypes = [C.c_void_p, C.POINTER(ExpandedProblem), C.POINTER(Params),
                                              C.POINTER(Solution)]
     L.bunmpc_centroidal_mats_host.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 9
+    L.bunmpc_measure_fp64_peak.argtypes = [C.c_void_p, dp]
+    L.bunmpc_selftest_division.argtypes = [C.c_void_p, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
     L.bunmpc_host_alloc.argtypes = [C.c_ulonglong]
     L.bunmpc_host_alloc.restype = C.c_void_p
     L.bunmpc_host_free.argtypes = [C.c_void_p]

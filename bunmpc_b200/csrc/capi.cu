@@ -144,7 +144,7 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     // symbolic tables
     HostTables hf = build_tables(pattern_Ax(n, e), nx, nf, 9 * e * n, 3 * e, 3, 2 * e, 3);
     HostTables hx = build_tables(pattern_Af(n), nx, nx, 27 * n + 9, 11, 4, 4, 4);
-    if (hf.KH > 3 * e || hf.PM > 3 || hf.KA > 2 * e || hf.KC > 3 || hx.KH > 11 || hx.PM > 4 || hx.KA > 4 || hx.KC > 4) {
+    if (!hf.contiguous_rows || hf.KH > 3 * e || hf.PM > 3 || hf.KA > 2 * e || hf.KC > 3 || hx.KH > 11 || hx.PM > 4 || hx.KA > 4 || hx.KC > 4) {
         delete s;
         return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: sparsity pattern exceeds the kernel's table bounds");
     }
@@ -235,7 +235,7 @@ int bunmpc_expand_device(bunmpc_solver *s, const bunmpc_compact_problem *p, doub
     if (!s || !p || !Qx || !qx || !Qf || !qf || !lbx || !ubx) return fail(BUNMPC_ERR_ARG, "expand: null argument");
     if (p->batch < 1) return fail(BUNMPC_ERR_ARG, "expand: batch < 1");
     CK(cudaSetDevice(s->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL is CUDA's default stream
     ExpandArgs a;
     a.B = p->batch; a.n = s->n; a.e = s->e; a.nx = s->nx; a.nf = s->nf;
     a.cnt_plan = mk(p->cnt_plan); a.W_X = mk(p->W_X); a.W_X_ter = mk(p->W_X_ter); a.X_nom = mk(p->X_nom);
@@ -262,7 +262,7 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
         !p->Qf.ptr || !p->qf.ptr || !p->lbx.ptr || !p->ubx.ptr || !p->L0.ptr)
         return fail(BUNMPC_ERR_ARG, "solve: null input field");
     CK(cudaSetDevice(s->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL is CUDA's default stream
     SolveArgs a;
     a.B = p->batch; a.n = s->n; a.e = s->e; a.nx = s->nx; a.nf = s->nf;
     a.m = mk(p->m); a.rho = mk(p->rho); a.x_init = mk(p->x_init); a.cnt_plan = mk(p->cnt_plan); a.dt = mk(p->dt);
@@ -452,6 +452,47 @@ int bunmpc_centroidal_mats_host(bunmpc_solver *s, double m, const double *cnt_pl
     if (A_f) CK(cudaMemcpyAsync(A_f, dAf, nx * nx * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (b_f) CK(cudaMemcpyAsync(b_f, dbf, nx * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return BUNMPC_OK;
+}
+
+int bunmpc_selftest_division(bunmpc_solver *s, long long n_pairs, unsigned long long seed, long long *mismatches)
+{
+    if (!s || !mismatches || n_pairs < 1) return fail(BUNMPC_ERR_ARG, "selftest: bad argument");
+    CK(cudaSetDevice(s->device));
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(s->out_d);
+    CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s->stream));
+    division_selftest_kernel<<<s->num_sms * 8, 256, 0, s->stream>>>(n_pairs, seed, d);
+    s->launches++;
+    CK(cudaGetLastError());
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *mismatches = (long long)h;
+    return BUNMPC_OK;
+}
+
+int bunmpc_measure_fp64_peak(bunmpc_solver *s, double *tflops)
+{
+    if (!s || !tflops) return fail(BUNMPC_ERR_ARG, "peak: null argument");
+    CK(cudaSetDevice(s->device));
+    const int iters = 4096, threads = 256, blocks = s->num_sms * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(e0, s->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, s->stream>>>(s->out_d, iters, 1.0 + rep);
+        CK(cudaEventRecord(e1, s->stream));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double)iters * (double)threads * (double)blocks;
+        const double tf = flops / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;    // rep 0 is the warm-up
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
     return BUNMPC_OK;
 }
 

@@ -22,6 +22,7 @@ struct Entry { int row, col, aidx; };
 struct HostTables {
     int nv = 0, nr = 0, nvp = 0, nrp = 0, nval = 0;
     int KH = 0, PM = 0, KA = 0, KC = 0;      // maxima found (must not exceed the kernel's template bounds)
+    bool contiguous_rows = true;             // every row of A^T A occupies consecutive columns
     std::vector<uint8_t> h_len, h_np, c_len, a_len;
     std::vector<uint16_t> h_col, c_row, c_aidx, a_col, a_aidx;
     std::vector<uint32_t> h_pair;
@@ -122,6 +123,8 @@ inline HostTables build_tables(const std::vector<Entry> &E, int nr, int nv, int 
         }
         T.KH = std::max(T.KH, k);
         if (k <= KH) T.h_len[i] = (uint8_t)k;
+        for (int q = 1; q < k && q < KH; ++q)
+            if (T.h_col[(size_t)q * T.nvp + i] != T.h_col[i] + q) T.contiguous_rows = false;
     }
     return T;
 }

@@ -70,6 +70,18 @@ class BatchSolver:
         _lib.check(_lib.lib().bunmpc_kernel_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return dict(ctas_per_sm=a.value, threads=b.value, smem_bytes=c.value, num_sms=d.value)
 
+    def measure_fp64_peak(self) -> float:
+        """TFLOP/s of a register-only DFMA micro-benchmark on this GPU (bench.py's FP64 roofline denominator)."""
+        v = C.c_double()
+        _lib.check(_lib.lib().bunmpc_measure_fp64_peak(self._h, C.byref(v)), "bunmpc_measure_fp64_peak")
+        return float(v.value)
+
+    def selftest_division(self, n_pairs: int = 1 << 24, seed: int = 1) -> int:
+        """Mismatches between the kernel's hoisted-reciprocal division and IEEE `/` on n_pairs operand pairs."""
+        v = C.c_longlong()
+        _lib.check(_lib.lib().bunmpc_selftest_division(self._h, int(n_pairs), int(seed), C.byref(v)), "selftest")
+        return int(v.value)
+
     def _widths(self):
         n, e, nx, nf = self.n_col, self.n_eff, self.nx, self.nf
         return dict(m=1, rho=1, x_init=9, cnt_plan=4 * e * n, dt=n, W_X=9 * n, W_X_ter=9, X_nom=9 * n, X_ter=9,

@@ -112,7 +112,7 @@ long long bunmpc_launch_count(const bunmpc_solver *s);
 /* CUDA occupancy of the solve kernel for this solver: CTAs per SM, threads per CTA, dynamic smem bytes */
 int  bunmpc_kernel_info(const bunmpc_solver *s, int *ctas_per_sm, int *threads, int *smem_bytes, int *num_sms);
 
-/* ---- device-pointer entry points: asynchronous on `stream` (a cudaStream_t; NULL = the solver's own).
+/* ---- device-pointer entry points: asynchronous on `stream` (a cudaStream_t; NULL = CUDA's default stream).
  *      All pointers in the structs are device pointers on the solver's device. ---- */
 
 /* create_bound_constraints + create_cost_X + create_cost_F for a batch (biconvex.cpp:27-78):
@@ -138,6 +138,14 @@ int bunmpc_solve_expanded_host(bunmpc_solver *s, const bunmpc_expanded_problem *
 int bunmpc_centroidal_mats_host(bunmpc_solver *s, double m, const double *cnt_plan, const double *dt,
                                 const double *X, const double *F, const double *x_init,
                                 double *A_x, double *b_x, double *A_f, double *b_f);
+
+/* Measurement aid for bench.py: FP64 FMA throughput of this GPU (TFLOP/s, 2 flops per DFMA) from a
+ * register-only DFMA micro-benchmark; the denominator of the FP64-pipe roofline. */
+int bunmpc_measure_fp64_peak(bunmpc_solver *s, double *tflops);
+
+/* Self-test of the hoisted-reciprocal division used for g/L in the FISTA step (kernels.cuh div_fast):
+ * compares it with IEEE division on n_pairs pseudo-random operand pairs, returns the number of mismatches. */
+int bunmpc_selftest_division(bunmpc_solver *s, long long n_pairs, unsigned long long seed, long long *mismatches);
 
 /* pinned host memory helpers for callers without a CUDA runtime of their own */
 void *bunmpc_host_alloc(unsigned long long bytes);
