@@ -44,7 +44,7 @@ class ExpandedProblem(C.Structure):
 
 class Solution(C.Structure):
     _fields_ = [("X", C.c_void_p), ("F", C.c_void_p), ("P", C.c_void_p), ("L", C.c_void_p), ("iters", C.c_void_p),
-                ("viol", C.c_void_p), ("status", C.c_void_p), ("viol_hist", C.c_void_p)]
+                ("viol", C.c_void_p), ("status", C.c_void_p), ("viol_hist", C.c_void_p), ("cycles", C.c_void_p)]
 
 
 # every symbol include/bunmpc.h declares

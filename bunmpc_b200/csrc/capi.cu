@@ -44,6 +44,7 @@ struct bunmpc_solver {
     double *ex = nullptr;            // expanded Qx,qx,lbx,ubx,Qf,qf
     double *out_d = nullptr;         // X,F,P,L,viol,(hist)
     int *out_i = nullptr;            // iters, status
+    long long *out_c = nullptr;      // cycles
     double *mats = nullptr;          // scratch for bunmpc_centroidal_mats_host
     long long launches = 0;
     int nthreads = 0, smem_bytes = 0, nav = 0;
@@ -82,25 +83,27 @@ static cudaError_t upload_tables(DevTables &D, const HostTables &H)
 typedef void (*solve_fn)(const SolveArgs);
 
 template <int NE, int ARITH>
-static solve_fn pick_kernel(int nthreads)
+static solve_fn pick_kernel(int n, int nthreads)
 {
-    if (nthreads <= 256) return solve_kernel<NE, ARITH, 256, 2>;
-    if (nthreads <= 384) return solve_kernel<NE, ARITH, 384, 1>;
-    if (nthreads <= 512) return solve_kernel<NE, ARITH, 512, 1>;
-    if (nthreads <= 768) return solve_kernel<NE, ARITH, 768, 1>;
-    return solve_kernel<NE, ARITH, 1024, 1>;
+    if (n == 20 && nthreads <= 288) return solve_kernel<NE, ARITH, 20, 288, 96>;   // BASELINE trot horizon
+    if (nthreads <= 288) return solve_kernel<NE, ARITH, 0, 288, 96>;
+    if (nthreads <= 416) return solve_kernel<NE, ARITH, 0, 416, 128>;
+    if (nthreads <= 544) return solve_kernel<NE, ARITH, 0, 544, 96>;
+    if (nthreads <= 800) return solve_kernel<NE, ARITH, 0, 800, 72>;
+    return solve_kernel<NE, ARITH, 0, 1024, 64>;
 }
 
-static solve_fn pick(int e, int arith, int nthreads)
+static solve_fn pick(int e, int arith, int n, int nthreads)
 {
-    if (e == 4) return arith ? pick_kernel<4, 1>(nthreads) : pick_kernel<4, 0>(nthreads);
+    if (e == 4) return arith ? pick_kernel<4, 1>(n, nthreads) : pick_kernel<4, 0>(n, nthreads);
     return nullptr;
 }
 
+// must mirror the carve-up at the top of solve_kernel
 static size_t smem_doubles(int n, int e, int max_inner, int nav)
 {
     int nx = 9 * (n + 1), nf = 3 * e * n, nm = nx > nf ? nx : nf;
-    return (size_t)nx * 4 + nf + 2 * (size_t)nm + nav + 4 * (size_t)e * n + n + max_inner + 8 * 32 + 4 + 2;
+    return (size_t)nx * 4 + nf + 2 * ((size_t)nm + 2) + nav + 4 * (size_t)e * n + n + 8 * 32 + 4 + 2 + max_inner;
 }
 
 extern "C" {
@@ -130,7 +133,7 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     if (n_eff != 4) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: kernels are built for n_eff == 4");
     const int n = n_col, e = n_eff, nx = 9 * (n + 1), nf = 3 * e * n;
     const int wf = (nf + 29) / 30, wx = (nx + 31) / 32;
-    const int nthreads = 32 * (wf > wx ? wf : wx);
+    const int nthreads = 32 * ((wf > wx ? wf : wx) + 1);   // worker warps + the scalar warp
     if (nthreads > 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: n_col too large for one CTA per instance");
     CK(cudaSetDevice(device));
     bunmpc_solver *s = new bunmpc_solver();
@@ -178,12 +181,13 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     CK(cudaMalloc(&s->ex, sizeof(double) * B * (4 * (size_t)nx + 2 * (size_t)nf)));
     CK(cudaMalloc(&s->out_d, sizeof(double) * B * (2 * (size_t)nx + nf + 3)));
     CK(cudaMalloc(&s->out_i, sizeof(int) * B * 6));
+    CK(cudaMalloc(&s->out_c, sizeof(long long) * B));
     CK(cudaMalloc(&s->mats, sizeof(double) * ((size_t)nx * nf + (size_t)nx * nx + 2 * (size_t)nx + 4 * (size_t)e * n + n + nx + nf + 9)));
 
     // opt in to the shared memory the kernel needs and record occupancy
     s->smem_bytes = (int)(smem_doubles(n, e, 150, s->nav) * sizeof(double));
     for (int arith = 0; arith < 2; ++arith) {
-        solve_fn fn = pick(e, arith, nthreads);
+        solve_fn fn = pick(e, arith, n, nthreads);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, nthreads, s->smem_bytes));
@@ -200,7 +204,7 @@ void bunmpc_destroy(bunmpc_solver *s)
     for (void *p : s->TF.allocs) cudaFree(p);
     for (void *p : s->TX.allocs) cudaFree(p);
     cudaFree(s->work_counter); cudaFree(s->coef); cudaFree(s->st_in); cudaFree(s->ex);
-    cudaFree(s->out_d); cudaFree(s->out_i); cudaFree(s->mats);
+    cudaFree(s->out_d); cudaFree(s->out_i); cudaFree(s->out_c); cudaFree(s->mats);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -269,13 +273,17 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     a.Qx = mk(p->Qx); a.qx = mk(p->qx); a.Qf = mk(p->Qf); a.qf = mk(p->qf); a.lbx = mk(p->lbx); a.ubx = mk(p->ubx);
     a.L0 = mk(p->L0); a.X0 = mk(p->X0); a.F0 = mk(p->F0); a.P0 = mk(p->P0);
     a.X = out->X; a.F = out->F; a.P = out->P; a.L = out->L; a.viol = out->viol; a.viol_hist = out->viol_hist;
-    a.iters = out->iters; a.status = out->status;
+    a.iters = out->iters; a.status = out->status; a.cycles = out->cycles; a.prof = nullptr;
+#ifdef BUNMPC_PHASE_PROF
+    a.prof = reinterpret_cast<long long *>(out->viol_hist);   // profiling build: viol_hist carries [B][16] counters
+    a.viol_hist = nullptr;
+#endif
     a.max_outer = prm->max_outer; a.max_inner = prm->max_inner;
     a.tol = prm->tol; a.exit_tol = prm->exit_tol; a.beta = prm->beta; a.mu = prm->mu;
     a.coef = s->coef; a.TF = s->TF.d; a.TX = s->TX.d; a.work_counter = s->work_counter; a.nav = s->nav;
     const int smem = (int)(smem_doubles(s->n, s->e, prm->max_inner, s->nav) * sizeof(double));
     if (smem > 200 * 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: shared memory need exceeds 200 KB");
-    solve_fn fn = pick(s->e, prm->arith, s->nthreads);
+    solve_fn fn = pick(s->e, prm->arith, s->n, s->nthreads);
     int per_sm = s->ctas_per_sm[prm->arith];
     if (smem != s->smem_bytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->nthreads, smem));
     if (per_sm < 1) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: kernel does not fit on an SM");
@@ -346,6 +354,7 @@ static int copy_out(bunmpc_solver *s, int B, const bunmpc_solution &dev, const b
     if (out->viol) CK(cudaMemcpyAsync(out->viol, dev.viol, Bs * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (out->iters) CK(cudaMemcpyAsync(out->iters, dev.iters, Bs * 5 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     if (out->status) CK(cudaMemcpyAsync(out->status, dev.status, Bs * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (out->cycles) CK(cudaMemcpyAsync(out->cycles, dev.cycles, Bs * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
     if (out->viol_hist)
         CK(cudaMemcpyAsync(out->viol_hist, dev.viol_hist, Bs * (size_t)max_outer * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -359,6 +368,7 @@ static int dev_solution(bunmpc_solver *s, int B, const bunmpc_solution *want, in
     dev->X = s->out_d; dev->F = dev->X + Bs * nx; dev->P = dev->F + Bs * nf; dev->L = dev->P + Bs * nx;
     dev->viol = dev->L + 2 * Bs;
     dev->iters = s->out_i; dev->status = s->out_i + 5 * Bs;
+    dev->cycles = want->cycles ? s->out_c : nullptr;
     dev->viol_hist = nullptr;
     *hist_alloc = nullptr;
     if (want->viol_hist) {

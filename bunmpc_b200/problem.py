@@ -136,6 +136,8 @@ class BatchSolution:
     viol: np.ndarray     # [B]       ||A_f X - b_f|| at exit
     status: np.ndarray   # [B]       0 converged, 1 max_outer reached, 2 NaN
     m: np.ndarray = None
+    cycles: np.ndarray = None      # [B] SM clock cycles spent per instance (in-kernel latency)
+    viol_hist: np.ndarray = None   # [B, max_outer] when requested
 
     def com(self):
         """return_opt_com, biconvex.cpp:122-130: [B, n+1, 3]"""

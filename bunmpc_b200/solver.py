@@ -116,11 +116,14 @@ class BatchSolver:
         L = o.get("L", np.empty((B, 2))); viol = o.get("viol", np.empty(B))
         iters = o.get("iters", np.empty((B, 5), dtype=np.int32)); status = o.get("status", np.empty(B, dtype=np.int32))
         hist = np.empty((B, prm.max_outer)) if viol_hist else None
+        cycles = o.get("cycles", np.empty(B, dtype=np.int64))
         sol = _lib.Solution(X.ctypes.data, F.ctypes.data, P.ctypes.data, L.ctypes.data, iters.ctypes.data,
-                            viol.ctypes.data, status.ctypes.data, hist.ctypes.data if viol_hist else None)
+                            viol.ctypes.data, status.ctypes.data, hist.ctypes.data if viol_hist else None,
+                            cycles.ctypes.data)
         _lib.check(_lib.lib().bunmpc_solve_compact_host(self._h, C.byref(prob), C.byref(prm), C.byref(sol)),
                    "bunmpc_solve_compact_host")
         res = BatchSolution(X=X, F=F, P=P, L=L, iters=iters, viol=viol, status=status, m=batch.m)
+        res.cycles = cycles
         if viol_hist:
             res.viol_hist = hist
         return res
@@ -150,7 +153,7 @@ class BatchSolver:
         iters, status = np.empty((B, 5), dtype=np.int32), np.empty(B, dtype=np.int32)
         hist = np.empty((B, prm.max_outer)) if viol_hist else None
         sol = _lib.Solution(X.ctypes.data, F.ctypes.data, P.ctypes.data, L.ctypes.data, iters.ctypes.data,
-                            viol.ctypes.data, status.ctypes.data, hist.ctypes.data if viol_hist else None)
+                            viol.ctypes.data, status.ctypes.data, hist.ctypes.data if viol_hist else None, None)
         _lib.check(_lib.lib().bunmpc_solve_expanded_host(self._h, C.byref(prob), C.byref(prm), C.byref(sol)),
                    "bunmpc_solve_expanded_host")
         res = BatchSolution(X=X, F=F, P=P, L=L, iters=iters, viol=viol, status=status, m=arrs["m"])
@@ -196,7 +199,8 @@ class BatchSolver:
                    L=torch.empty((B, 2), dtype=torch.float64, device=dev),
                    iters=torch.empty((B, 5), dtype=torch.int32, device=dev),
                    viol=torch.empty((B,), dtype=torch.float64, device=dev),
-                   status=torch.empty((B,), dtype=torch.int32, device=dev))
+                   status=torch.empty((B,), dtype=torch.int32, device=dev),
+                   cycles=torch.empty((B,), dtype=torch.int64, device=dev))
         return DeviceBatch(B=B, fields=fields, out=out, widths=w)
 
     def solve_resident(self, dev: DeviceBatch, params: Optional[SolverParams] = None,
@@ -211,7 +215,8 @@ class BatchSolver:
                     _lib.In(t.data_ptr(), 0 if t.shape[0] == 1 else dev.widths[f]))
         o = dev.out
         sol = _lib.Solution(o["X"].data_ptr(), o["F"].data_ptr(), o["P"].data_ptr(), o["L"].data_ptr(),
-                            o["iters"].data_ptr(), o["viol"].data_ptr(), o["status"].data_ptr(), None)
+                            o["iters"].data_ptr(), o["viol"].data_ptr(), o["status"].data_ptr(), None,
+                            o["cycles"].data_ptr())
         prm = _c_params(params, arith)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib().bunmpc_solve_compact_device(self._h, C.byref(prob), C.byref(prm), C.byref(sol),

@@ -96,6 +96,7 @@ typedef struct {
     double *viol;       /* [B]      ||A_f X - b_f|| of the last outer iteration */
     int    *status;     /* [B]      BUNMPC_CONVERGED / MAX_ITERS / NAN */
     double *viol_hist;  /* [B][max_outer] return_dyn_viol_hist (collect_statistics), NaN-padded */
+    long long *cycles;  /* [B]      SM clock cycles the instance's CTA spent on it (in-kernel solve latency) */
 } bunmpc_solution;
 
 int         bunmpc_version(void);
