@@ -82,14 +82,14 @@ static cudaError_t upload_tables(DevTables &D, const HostTables &H)
 // ---- kernel dispatch: thread-count classes with their own register budgets ----
 typedef void (*solve_fn)(const SolveArgs);
 
+// thread-count classes: threads = 32 (variable warps + row warps + 1 scalar warp); the register cap is what
+// lets two CTAs share an SM (the register file is split over 4 schedulers of 16K registers each)
 template <int NE, int ARITH>
 static solve_fn pick_kernel(int n, int nthreads)
 {
-    if (n == 20 && nthreads <= 288) return solve_kernel<NE, ARITH, 20, 288, 96>;   // BASELINE trot horizon
-    if (nthreads <= 288) return solve_kernel<NE, ARITH, 0, 288, 96>;
-    if (nthreads <= 416) return solve_kernel<NE, ARITH, 0, 416, 128>;
-    if (nthreads <= 544) return solve_kernel<NE, ARITH, 0, 544, 96>;
-    if (nthreads <= 800) return solve_kernel<NE, ARITH, 0, 800, 72>;
+    if (n == 20 && nthreads <= 480) return solve_kernel<NE, ARITH, 20, 480, 128>;   // BASELINE trot horizon
+    if (nthreads <= 512) return solve_kernel<NE, ARITH, 0, 512, 64>;
+    if (nthreads <= 768) return solve_kernel<NE, ARITH, 0, 768, 80>;
     return solve_kernel<NE, ARITH, 0, 1024, 64>;
 }
 
@@ -103,7 +103,8 @@ static solve_fn pick(int e, int arith, int n, int nthreads)
 static size_t smem_doubles(int n, int e, int max_inner, int nav)
 {
     int nx = 9 * (n + 1), nf = 3 * e * n, nm = nx > nf ? nx : nf;
-    return (size_t)nx * 4 + nf + 2 * ((size_t)nm + 2) + nav + 4 * (size_t)e * n + n + 8 * 32 + 4 + 2 + max_inner;
+    return (size_t)nx * 4 + nf + 4 * ((size_t)nm + 2) + nav + 4 * (size_t)e * n + n + 3 * 4 * 32 + 3 * 2 * 32 + 4 + 2
+           + max_inner;
 }
 
 extern "C" {
@@ -133,7 +134,7 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     if (n_eff != 4) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: kernels are built for n_eff == 4");
     const int n = n_col, e = n_eff, nx = 9 * (n + 1), nf = 3 * e * n;
     const int wf = (nf + 29) / 30, wx = (nx + 31) / 32;
-    const int nthreads = 32 * ((wf > wx ? wf : wx) + 1);   // worker warps + the scalar warp
+    const int nthreads = 32 * ((wf > wx ? wf : wx) + wx + 1);   // variable warps + row warps + the scalar warp
     if (nthreads > 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: n_col too large for one CTA per instance");
     CK(cudaSetDevice(device));
     bunmpc_solver *s = new bunmpc_solver();
@@ -275,7 +276,7 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     a.X = out->X; a.F = out->F; a.P = out->P; a.L = out->L; a.viol = out->viol; a.viol_hist = out->viol_hist;
     a.iters = out->iters; a.status = out->status; a.cycles = out->cycles; a.prof = nullptr;
 #ifdef BUNMPC_PHASE_PROF
-    a.prof = reinterpret_cast<long long *>(out->viol_hist);   // profiling build: viol_hist carries [B][16] counters
+    a.prof = reinterpret_cast<long long *>(out->viol_hist);   // profiling build: the viol_hist buffer carries [B][64] counters
     a.viol_hist = nullptr;
 #endif
     a.max_outer = prm->max_outer; a.max_inner = prm->max_inner;

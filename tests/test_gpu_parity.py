@@ -53,3 +53,28 @@ def test_fma_mode_matches_fma_oracle(oracle):
     sol = BatchSolver(b.n_col, b.n_eff, max_batch=32).solve(b, arith=ARITH_FMA)
     ref = oracle.solve(b, params=oracle.default_params(use_fma=1), n_threads=8)
     assert_same(sol, ref, "fma")
+
+
+def test_line_search_rejections_replay(oracle):
+    """Tiny initial step sizes force many line-search rejections (L *= 1.5), which sends the kernel's
+    speculative pipeline through its sequential-replay path; counters and iterates must still match."""
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.perturbed(16, "solo12", "trot", seed=7)
+    b.L0 = np.array([[1.0, 40.0]])
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=16).solve(b)
+    ref = oracle.solve(b, n_threads=8)
+    assert ref["iters"][:, 3].min() > 5 and ref["iters"][:, 4].min() > 5     # rejections did happen
+    assert_same(sol, ref, "rejections")
+
+
+def test_go2_mass_hits_cap_and_backtracks(oracle):
+    """Solo-tuned weights with the Go2 mass: iteration cap and occasional L_x backtracks."""
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.perturbed(16, "go2", "trot", seed=11)
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=16).solve(b)
+    ref = oracle.solve(b, n_threads=8)
+    assert_same(sol, ref, "go2")
