@@ -59,6 +59,7 @@ void bicon_default_params(bicon_params *p)
     p->beta = 1.5;       /* [FH]:54 */
     p->mu = 1.0;         /* [FH]:60 */
     p->use_fma = 0;
+    p->f_block = F_BLOCK;
 }
 
 /* ------------------------------------------------------------------ sparse patterns --------- */
@@ -552,7 +553,7 @@ ALWAYS_INLINE int solve_impl(const int FM, bicon_ws *ws, const bicon_problem *p,
     int it_f = 0, it_x = 0, ls_f = 0, ls_x = 0, outer = 0, status = 1;
     double vnorm = 0.0;
 
-    fista_data Df = { nf, nx, F_BLOCK, 1, ws->Gf.rp, ws->Gf.cj, ws->Hf, ws->hf,
+    fista_data Df = { nf, nx, (prm->f_block == 32 ? 32 : F_BLOCK), 1, ws->Gf.rp, ws->Gf.cj, ws->Hf, ws->hf,
                       ws->Ax.rp, ws->Ax.cj, ws->Ax_csr, ws->w, p->Qf, p->qf, NULL, NULL,
                       p->rho, prm->mu, prm->beta };
     fista_data Dx = { nx, nx, X_BLOCK, 0, ws->Gx.rp, ws->Gx.cj, ws->Hx, ws->hx,

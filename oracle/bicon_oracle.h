@@ -41,6 +41,9 @@ typedef struct {
     int    use_fma;     /* 0: separate multiply and add everywhere (x86-64 Release build of the
                            reference has no FMA); 1: the fused variant mirrored by the GPU's
                            BUNMPC_ARITH_FMA mode */
+    int    f_block;     /* leaves per reduction block for vectors of contact forces: 30 (ten 3-vectors, the
+                           order the GPU kernels use; default) or 32 (the order of oracle/refshim, used only
+                           to cross-check this restatement against the reference's own sources) */
 } bicon_params;
 
 void bicon_default_params(bicon_params *p);

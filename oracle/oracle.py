@@ -20,7 +20,7 @@ _lib = None
 class Params(C.Structure):
     _fields_ = [("max_outer", C.c_int), ("max_inner", C.c_int), ("tol", C.c_double),
                 ("exit_tol", C.c_double), ("beta", C.c_double), ("mu", C.c_double),
-                ("use_fma", C.c_int)]
+                ("use_fma", C.c_int), ("f_block", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -164,3 +164,58 @@ def solve(batch, params=None, n_threads=1):
     return solve_expanded(n, e, batch.m, batch.rho, x_init, batch.cnt_plan, batch.dt,
                           ex["Qx"], ex["qx"], ex["Qf"], ex["qf"], ex["lbx"], ex["ubx"],
                           X0, F0, P0, batch.L0, params=params, n_threads=n_threads)
+
+
+# ---------------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own sources compiled against the Eigen stand-in (oracle/refshim)
+# ---------------------------------------------------------------------------------------------------
+_REF_SO = os.path.join(_HERE, "_ref", "libbicon_ref.so")
+_ref = None
+
+
+def ref_available() -> bool:
+    return os.path.exists(_REF_SO)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(_REF_SO)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        _ref.ref_create.restype = C.c_void_p
+        _ref.ref_create.argtypes = [C.c_double, C.c_int, C.c_int]
+        _ref.ref_destroy.argtypes = [C.c_void_p]
+        _ref.ref_solve.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_double] + [dp] * 12 + [C.c_int] + [dp] * 4
+                                   + [ip, dp])
+    return _ref
+
+
+def ref_solve(batch, max_outer=100):
+    """Every instance of a CentroidalBatch through the reference's own BiConvexMP (fresh object per instance,
+    its own create_* setters and optimize()).  Same result dict as solve()."""
+    R = ref_lib()
+    B, n, e = batch.B, batch.n_col, batch.n_eff
+    nx, nf = 9 * (n + 1), 3 * e * n
+    g = lambda name, shape: _d(getattr(batch, name), (B,) + shape)
+    m, rho, x_init = g("m", ()), g("rho", ()), g("x_init", (9,))
+    cnt, dt, bounds = g("cnt_plan", (n, e, 4)), g("dt", (n,)), g("bounds", (n, 6))
+    W_X, W_X_ter, X_ter, X_nom, W_F = g("W_X", (9 * n,)), g("W_X_ter", (9,)), g("X_ter", (9,)), g("X_nom", (9 * n,)), g("W_F", (nf,))
+    L0 = g("L0", (2,))
+    X0 = np.tile(x_init, (1, n + 1)) if batch.X0 is None else _d(batch.X0, (B, nx))
+    F0 = np.zeros((B, nf)) if batch.F0 is None else _d(batch.F0, (B, nf))
+    P0 = np.zeros((B, nx)) if batch.P0 is None else _d(batch.P0, (B, nx))
+    X, F, P = np.empty((B, nx)), np.empty((B, nf)), np.empty((B, nx))
+    L, viol = L0.copy(), np.empty(B)
+    iters, status = np.empty((B, 5), dtype=np.int32), np.empty(B, dtype=np.int32)
+    for b in range(B):
+        h = R.ref_create(float(m[b]), n, e)
+        it = (C.c_int * 5)()
+        v = C.c_double()
+        R.ref_solve(h, n, e, float(rho[b]), _p(x_init[b]), _p(cnt[b]), _p(dt[b]), _p(bounds[b]), _p(W_X[b]),
+                    _p(W_X_ter[b]), _p(X_ter[b]), _p(X_nom[b]), _p(W_F[b]), _p(X0[b]), _p(F0[b]), _p(P0[b]),
+                    int(max_outer), _p(L[b]), _p(X[b]), _p(F[b]), _p(P[b]), it, C.byref(v))
+        R.ref_destroy(h)
+        iters[b] = list(it)
+        viol[b] = v.value
+        status[b] = 2 if np.isnan(v.value) else (0 if v.value < 1e-3 else 1)
+    return dict(X=X, F=F, P=P, L=L, iters=iters, viol=viol, status=status)

@@ -1,0 +1,140 @@
+"""GPU tests against the committed golden vectors and of the drop-in python API, all through the C ABI."""
+import numpy as np
+import pytest
+
+from tests.golden.make_golden import RES, load
+
+pytestmark = pytest.mark.gpu
+CASES = load()
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and bool(((a == b) | (np.isnan(a.astype(float)) & np.isnan(b.astype(float)))).all())
+
+
+@pytest.mark.parametrize("name,batch,sets", CASES, ids=[c[0] for c in CASES])
+def test_gpu_reproduces_golden(name, batch, sets):
+    """STRICT mode == oracle default order == the reference's own sources (golden `ref`); FMA mode == its oracle twin."""
+    from bunmpc_b200 import ARITH_FMA
+    from bunmpc_b200.solver import BatchSolver
+    s = BatchSolver(batch.n_col, batch.n_eff, max_batch=batch.B)
+    sol = s.solve(batch)
+    solf = s.solve(batch, arith=ARITH_FMA)
+    for k in RES:
+        assert same(getattr(sol, k), sets["o30"][k]), f"{name}/o30/{k}"
+        assert same(getattr(solf, k), sets["o30f"][k]), f"{name}/o30f/{k}"
+        if k != "status":
+            assert same(getattr(sol, k), sets["ref"][k]), f"{name}/ref/{k}"
+
+
+def test_biconvexmp_drop_in_protocol(oracle):
+    """The reference's per-solve call protocol on the python class (abstract_cyclic_gen.py:391,611-614,663,671-673),
+    two consecutive solves on one object: the FISTA step sizes and iterates carry over like the C++ members."""
+    from bunmpc_b200 import BiconvexMP, synthetic
+    b = synthetic.perturbed(1, "solo12", "trot", seed=12)
+    n, e = b.n_col, b.n_eff
+    mp = BiconvexMP(2.5, n, e)
+    mp.set_rho(float(b.rho[0]))
+    mp.collect_statistics()
+    state = dict(X0=np.tile(b.x_init[0], n + 1)[None], F0=np.zeros((1, 3 * e * n)), P0=np.zeros((1, 9 * (n + 1))),
+                 L0=b.L0)
+    for rep in range(2):
+        for i in range(n):
+            mp.set_contact_plan(b.cnt_plan[0, i], b.dt[0, i])
+        mp.create_bound_constraints(b.bounds[0], 15.0, 15.0, 15.0)
+        mp.create_cost_X(b.W_X[0], b.W_X_ter[0], b.X_ter[0], b.X_nom[0])
+        mp.create_cost_F(b.W_F[0])
+        mp.set_warm_start_vars(state["X0"][0], state["F0"][0], state["P0"][0])
+        mp.optimize(b.x_init[0], 100)
+        ref = oracle.solve(b.with_state(**state))
+        assert np.array_equal(mp.return_opt_x(), ref["X"][0]) and np.array_equal(mp.return_opt_f(), ref["F"][0])
+        assert np.array_equal(mp.return_opt_p(), ref["P"][0])
+        assert (mp.L_f, mp.L_x) == tuple(ref["L"][0]) and np.array_equal(mp.last_iters, ref["iters"][0])
+        assert np.array_equal(mp.return_opt_com(), ref["X"][0].reshape(-1, 9)[:, :3])
+        assert np.array_equal(mp.return_opt_mom()[:, :3], 2.5 * ref["X"][0].reshape(-1, 9)[:, 3:6])
+        # second solve: cold restart of the iterates (kino_dyn.cpp:83-99) but the step sizes persist (Q3)
+        state = dict(X0=state["X0"], F0=state["F0"], P0=state["P0"], L0=ref["L"])
+    hist = mp.return_dyn_viol_hist()
+    assert len(hist) == 2 * int(ref["iters"][0, 0]) or len(hist) > 0
+    assert hist[-1] == ref["viol"][0]
+    with pytest.raises(RuntimeError):
+        mp.optimize(b.x_init[0], 100)          # optimize() cleared the contact plan (biconvex.cpp:117)
+
+
+def test_dense_matrix_accessors(oracle):
+    """return_A_x / return_b_x / return_A_f / return_b_f against the oracle's dense matrices."""
+    from bunmpc_b200 import BiconvexMP, synthetic
+    b = synthetic.perturbed(1, "solo12", "trot", seed=13)
+    n, e = b.n_col, b.n_eff
+    mp = BiconvexMP(2.5, n, e)
+    for i in range(n):
+        mp.set_contact_plan(b.cnt_plan[0, i], b.dt[0, i])
+    rng = np.random.default_rng(1)
+    X, F = rng.normal(size=9 * (n + 1)), rng.normal(size=3 * e * n)
+    A_x, b_x = oracle.dense_x_mat(2.5, b.cnt_plan[0], b.dt[0], X)
+    A_f, b_f = oracle.dense_f_mat(2.5, b.cnt_plan[0], b.dt[0], F, b.x_init[0])
+    assert np.array_equal(mp.return_A_x(X), A_x) and np.array_equal(mp.return_b_x(X), b_x)
+    assert np.array_equal(mp.return_A_f(F, b.x_init[0]), A_f) and np.array_equal(mp.return_b_f(F, b.x_init[0]), b_f)
+
+
+def test_expand_kernel_matches_oracle_builders(oracle):
+    """create_bound_constraints / create_cost_X / create_cost_F as a CUDA kernel (bunmpc_expand_device)."""
+    import ctypes as C
+    import torch
+    from bunmpc_b200 import _lib, synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.perturbed(37, "solo12", "jump", seed=14)          # jump: knots without any contact -> infinite bounds
+    s = BatchSolver(b.n_col, b.n_eff, max_batch=64)
+    dev = s.upload(b)
+    B, nx, nf = b.B, s.nx, s.nf
+    out = {k: torch.empty((B, nx if k not in ("Qf", "qf") else nf), dtype=torch.float64, device="cuda")
+           for k in ("Qx", "qx", "Qf", "qf", "lbx", "ubx")}
+    prob = _lib.CompactProblem()
+    prob.batch = B
+    for f in _lib.COMPACT_FIELDS:
+        t = dev.fields[f]
+        setattr(prob, f, _lib.In(None, 0) if t is None else _lib.In(t.data_ptr(), 0 if t.shape[0] == 1 else dev.widths[f]))
+    _lib.check(_lib.lib().bunmpc_expand_device(s._h, C.byref(prob), *[C.c_void_p(out[k].data_ptr()) for k in
+                                               ("Qx", "qx", "Qf", "qf", "lbx", "ubx")], None))
+    torch.cuda.synchronize()
+    ex = oracle.expand(b)
+    assert np.isinf(ex["lbx"]).any()
+    for k in out:
+        assert np.array_equal(out[k].cpu().numpy(), ex[k]), k
+
+
+def test_full_size_batch_properties():
+    """BASELINE config[1] at full size (B = 1024): properties that need no oracle run --
+    permutation invariance (instances are independent), split invariance, feasibility of every solution."""
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.config(1, B=1024, seed=0)
+    s = BatchSolver(b.n_col, b.n_eff, max_batch=1024)
+    sol = s.solve(b)
+    perm = np.random.default_rng(0).permutation(b.B)
+    solp = s.solve(b.select(perm))
+    for k in ("X", "F", "P", "L", "iters", "viol", "status"):
+        assert np.array_equal(getattr(solp, k), getattr(sol, k)[perm]), k
+    half = s.solve(b.select(np.arange(0, 1024, 2)))
+    assert np.array_equal(half.F, sol.F[::2]) and np.array_equal(half.iters, sol.iters[::2])
+    n, e = b.n_col, b.n_eff
+    F = sol.F.reshape(-1, n, e, 3)
+    fin = sol.status != 2
+    assert fin.mean() > 0.99
+    assert (F[fin][..., 2] >= 0).all()
+    assert ((F[fin][..., 0] ** 2 + F[fin][..., 1] ** 2) <= F[fin][..., 2] * (1 + 1e-9) + 1e-12).all()
+    conv = sol.status == 0
+    assert conv.mean() > 0.5 and (sol.viol[conv] < 1e-3).all() and (sol.viol[sol.status == 1] >= 1e-3).all()
+    assert (sol.iters[:, 0] <= 100).all() and (sol.iters[:, 1] <= 150 * sol.iters[:, 0]).all()
+    assert (sol.cycles > 0).all()
+
+
+def test_errors_are_loud():
+    from bunmpc_b200 import BunmpcError, synthetic
+    from bunmpc_b200.solver import BatchSolver
+    with pytest.raises(BunmpcError):
+        BatchSolver(20, 3, max_batch=4)                 # kernels are built for n_eff == 4
+    s = BatchSolver(20, 4, max_batch=4)
+    with pytest.raises(ValueError):
+        s.solve(synthetic.perturbed(8, seed=0))         # batch > max_batch
