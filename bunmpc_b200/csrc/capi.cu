@@ -48,6 +48,7 @@ struct bunmpc_solver {
     double *mats = nullptr;          // scratch for bunmpc_centroidal_mats_host
     long long launches = 0;
     int nthreads = 0, smem_bytes = 0, nav = 0;
+    bool comb = false;               // combined warp roles (long horizons)
     int ctas_per_sm[2] = {0, 0};     // per arith
 };
 
@@ -84,18 +85,23 @@ typedef void (*solve_fn)(const SolveArgs);
 
 // thread-count classes: threads = 32 (variable warps + row warps + 1 scalar warp); the register cap is what
 // lets two CTAs share an SM (the register file is split over 4 schedulers of 16K registers each)
+// split roles: threads = 32 (variable warps + row warps + 1); combined roles (long horizons): 32 (variable warps + 1)
 template <int NE, int ARITH>
-static solve_fn pick_kernel(int n, int nthreads)
+static solve_fn pick_kernel2(int n, int nthreads, bool comb)
 {
-    if (n == 20 && nthreads <= 480) return solve_kernel<NE, ARITH, 20, 480, 128>;   // BASELINE trot horizon
-    if (nthreads <= 512) return solve_kernel<NE, ARITH, 0, 512, 64>;
-    if (nthreads <= 768) return solve_kernel<NE, ARITH, 0, 768, 80>;
-    return solve_kernel<NE, ARITH, 0, 1024, 64>;
+    if (comb) {
+        if (nthreads <= 768) return solve_kernel<NE, ARITH, 0, true, 768, 80>;
+        return solve_kernel<NE, ARITH, 0, true, 1024, 64>;
+    }
+    if (n == 20 && nthreads <= 480) return solve_kernel<NE, ARITH, 20, false, 480, 128>;   // BASELINE trot horizon
+    if (nthreads <= 512) return solve_kernel<NE, ARITH, 0, false, 512, 128>;
+    if (nthreads <= 768) return solve_kernel<NE, ARITH, 0, false, 768, 80>;
+    return solve_kernel<NE, ARITH, 0, false, 1024, 64>;
 }
 
-static solve_fn pick(int e, int arith, int n, int nthreads)
+static solve_fn pick(int e, int arith, int n, int nthreads, bool comb)
 {
-    if (e == 4) return arith ? pick_kernel<4, 1>(n, nthreads) : pick_kernel<4, 0>(n, nthreads);
+    if (e == 4) return arith ? pick_kernel2<4, 1>(n, nthreads, comb) : pick_kernel2<4, 0>(n, nthreads, comb);
     return nullptr;
 }
 
@@ -134,12 +140,15 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     if (n_eff != 4) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: kernels are built for n_eff == 4");
     const int n = n_col, e = n_eff, nx = 9 * (n + 1), nf = 3 * e * n;
     const int wf = (nf + 29) / 30, wx = (nx + 31) / 32;
-    const int nthreads = 32 * ((wf > wx ? wf : wx) + wx + 1);   // variable warps + row warps + the scalar warp
+    const int nvw = wf > wx ? wf : wx;
+    const bool comb = nvw + wx + 1 > 32;                   // too many warps for split roles: combine them
+    const int nthreads = 32 * (comb ? nvw + 1 : nvw + wx + 1);   // variable warps (+ row warps) + the scalar warp
     if (nthreads > 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: n_col too large for one CTA per instance");
     CK(cudaSetDevice(device));
     bunmpc_solver *s = new bunmpc_solver();
     s->device = device; s->n = n; s->e = e; s->nx = nx; s->nf = nf; s->max_batch = max_batch;
     s->nthreads = nthreads;
+    s->comb = comb;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     s->num_sms = prop.multiProcessorCount;
@@ -188,7 +197,7 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     // opt in to the shared memory the kernel needs and record occupancy
     s->smem_bytes = (int)(smem_doubles(n, e, 150, s->nav) * sizeof(double));
     for (int arith = 0; arith < 2; ++arith) {
-        solve_fn fn = pick(e, arith, n, nthreads);
+        solve_fn fn = pick(e, arith, n, nthreads, comb);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, nthreads, s->smem_bytes));
@@ -284,7 +293,7 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     a.coef = s->coef; a.TF = s->TF.d; a.TX = s->TX.d; a.work_counter = s->work_counter; a.nav = s->nav;
     const int smem = (int)(smem_doubles(s->n, s->e, prm->max_inner, s->nav) * sizeof(double));
     if (smem > 200 * 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: shared memory need exceeds 200 KB");
-    solve_fn fn = pick(s->e, prm->arith, s->n, s->nthreads);
+    solve_fn fn = pick(s->e, prm->arith, s->n, s->nthreads, s->comb);
     int per_sm = s->ctas_per_sm[prm->arith];
     if (smem != s->smem_bytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->nthreads, smem));
     if (per_sm < 1) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: kernel does not fit on an SM");

@@ -78,3 +78,17 @@ def test_go2_mass_hits_cap_and_backtracks(oracle):
     sol = BatchSolver(b.n_col, b.n_eff, max_batch=16).solve(b)
     ref = oracle.solve(b, n_threads=8)
     assert_same(sol, ref, "go2")
+
+
+@pytest.mark.parametrize("gait,scale,n_expected", [("trot", 2.0, 40), ("bound", 2.0, 48), ("jump", 2.0, 60)])
+def test_longer_horizons(oracle, gait, scale, n_expected):
+    """BASELINE config 4: longer horizons (gait_horizon x2 as in analysis/solve_times_test.py:60-66).
+    n = 40 still fits the split warp roles; n = 48 and 60 run with combined roles."""
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.perturbed(6, "solo12", gait, seed=17, horizon_scale=scale)
+    assert b.n_col == n_expected
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=8).solve(b)
+    ref = oracle.solve(b, n_threads=8)
+    assert_same(sol, ref, f"{gait} n={n_expected}")
