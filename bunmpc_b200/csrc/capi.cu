@@ -155,15 +155,17 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 
     // symbolic tables
-    HostTables hf = build_tables(pattern_Ax(n, e), nx, nf, 9 * e * n, 3 * e, 3, 2 * e, 3);
-    HostTables hx = build_tables(pattern_Af(n), nx, nx, 27 * n + 9, 11, 4, 4, 4);
+    const int nav0 = (9 * e * n > 27 * n + 9) ? 9 * e * n : 27 * n + 9;   // value index nav0 and iterate slot nm hold 0
+    const int nm0 = nx > nf ? nx : nf;
+    HostTables hf = build_tables(pattern_Ax(n, e), nx, nf, 9 * e * n, 3 * e, 3, 2 * e, 3, nav0, nm0);
+    HostTables hx = build_tables(pattern_Af(n), nx, nx, 27 * n + 9, 11, 4, 4, 4, nav0, nm0);
     if (!hf.contiguous_rows || hf.KH > 3 * e || hf.PM > 3 || hf.KA > 2 * e || hf.KC > 3 || hx.KH > 11 || hx.PM > 4 || hx.KA > 4 || hx.KC > 4) {
         delete s;
         return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: sparsity pattern exceeds the kernel's table bounds");
     }
     CK(upload_tables(s->TF, hf));
     CK(upload_tables(s->TX, hx));
-    s->nav = (9 * e * n > 27 * n + 9) ? 9 * e * n : 27 * n + 9;
+    s->nav = nav0 + 2;   // + the always-zero element the padded table entries point at
 
     // FISTA momentum coefficients (t_k - 1)/t_{k+1} with t_{k+1} = 1 + sqrt(1 + 4 t_k^2)/2 (fista.cpp:34-35, sic);
     // the sequence does not depend on the data, so it is tabulated once (IEEE sqrt and / are exact on both sides).

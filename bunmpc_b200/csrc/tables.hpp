@@ -58,8 +58,11 @@ inline std::vector<Entry> pattern_Af(int n)
 }
 
 // Tables in [slot][index] layout (coalesced when thread <-> index), leading dimension padded to 32.
+// Unused slots are PADDED so that the kernel can walk every table without branches: value indices point at
+// `zero_aidx` (an always-zero element of the value array), columns at `zero_col` (an always-zero element of the
+// iterate vectors), rows at row 0 (multiplied by a zero value).
 inline HostTables build_tables(const std::vector<Entry> &E, int nr, int nv, int nval,
-                               int KH, int PM, int KA, int KC)
+                               int KH, int PM, int KA, int KC, int zero_aidx, int zero_col)
 {
     HostTables T;
     T.nv = nv; T.nr = nr; T.nval = nval;
@@ -70,10 +73,11 @@ inline HostTables build_tables(const std::vector<Entry> &E, int nr, int nv, int 
     for (auto &v : byRow) std::sort(v.begin(), v.end(), [](const Entry &a, const Entry &b) { return a.col < b.col; });
 
     T.h_len.assign(T.nvp, 0); T.c_len.assign(T.nvp, 0); T.a_len.assign(T.nrp, 0);
-    T.h_col.assign((size_t)KH * T.nvp, 0); T.h_np.assign((size_t)KH * T.nvp, 0);
-    T.h_pair.assign((size_t)KH * PM * T.nvp, 0);
-    T.c_row.assign((size_t)KC * T.nvp, 0); T.c_aidx.assign((size_t)KC * T.nvp, 0);
-    T.a_col.assign((size_t)KA * T.nrp, 0); T.a_aidx.assign((size_t)KA * T.nrp, 0);
+    const uint32_t zpair = (uint32_t)zero_aidx | ((uint32_t)zero_aidx << 16);
+    T.h_col.assign((size_t)KH * T.nvp, (uint16_t)zero_col); T.h_np.assign((size_t)KH * T.nvp, 0);
+    T.h_pair.assign((size_t)KH * PM * T.nvp, zpair);
+    T.c_row.assign((size_t)KC * T.nvp, 0); T.c_aidx.assign((size_t)KC * T.nvp, (uint16_t)zero_aidx);
+    T.a_col.assign((size_t)KA * T.nrp, (uint16_t)zero_col); T.a_aidx.assign((size_t)KA * T.nrp, (uint16_t)zero_aidx);
 
     for (int r = 0; r < nr; ++r) {                       // rows of A, ascending column
         int len = (int)byRow[r].size();
