@@ -123,6 +123,32 @@ def run_cpu(batch, cores, max_instances, budget_s=25.0):
     return n / dt, n, dt
 
 
+def other_workloads(device, arith):
+    """Short single-GPU runs of the other BASELINE.json configs (per-GPU shard sizes), host-buffer path, one warm-up
+    + one timed solve each: reported for context, not part of `value`."""
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    out = {}
+    cases = [("config2_go2_trot_B2048_n20 (16384/8 GPUs)", lambda: synthetic.config(2, B=2048)),
+             ("config3_go2_bound_B512_n48 (reference algorithm diverges: cone quirk Q2, see DESIGN.md 6)", lambda: synthetic.config(3, B=512)),
+             ("solo12_bound_B1024_n48 (config 3 gait and horizon, Solo12 mass)", lambda: synthetic.perturbed(1024, "solo12", "bound", seed=0, horizon_scale=2.0)),
+             ("solo12_jump_B512_n60", lambda: synthetic.perturbed(512, "solo12", "jump", seed=0, horizon_scale=2.0)),
+             ("config4_bayes_goal+weight_samples_B8192_n20 (65536/8 GPUs)", lambda: synthetic.config(4, B=8192)),
+             ("solo12_trot_B8192_n20 (saturated)", lambda: synthetic.config(1, B=8192, seed=1))]
+    for name, make in cases:
+        b = make()
+        s = BatchSolver(b.n_col, b.n_eff, max_batch=b.B, device=device)
+        s.solve(b.select(np.arange(min(b.B, 256))), arith=arith)
+        t0 = time.perf_counter()
+        sol = s.solve(b, arith=arith)
+        dt = time.perf_counter() - t0
+        out[name] = {"solves_per_s_e2e": b.B / dt, "ms": 1e3 * dt, "n_col": b.n_col,
+                     "outer_mean": float(sol.iters[:, 0].mean()), "inner_mean": float(sol.iters[:, 1:3].sum(1).mean()),
+                     "converged_frac": float((sol.status == 0).mean()), "nan_frac": float((sol.status == 2).mean())}
+        s.close()
+    return out
+
+
 def reference_arm(args, rank, world):
     """--impl reference: the CPU implementation of the path on the host cores (oracle port; the reference's own
     sources need Eigen, which this image does not have).  Rank 0 alone runs and prints."""
@@ -160,6 +186,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="instances per GPU per step")
     ap.add_argument("--arith", default="strict", choices=["strict", "fma"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -330,6 +357,8 @@ def main():
                          "frac": hbm_ach / hbm_peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
     }
+    if not args.no_extra:
+        line["other_workloads"] = other_workloads(local_rank, arith)
     if not args.no_cpu:
         cores = cpu_cores()
         v, n, dt = run_cpu(synthetic.config(1, B=B, seed=0), cores, B, budget_s=25.0)

@@ -109,7 +109,7 @@ static solve_fn pick(int e, int arith, int n, int nthreads, bool comb)
 static size_t smem_doubles(int n, int e, int max_inner, int nav)
 {
     int nx = 9 * (n + 1), nf = 3 * e * n, nm = nx > nf ? nx : nf;
-    return (size_t)nx * 4 + nf + 4 * ((size_t)nm + 2) + nav + 4 * (size_t)e * n + n + 3 * 4 * 32 + 3 * 2 * 32 + 4 + 2
+    return (size_t)nx * 4 + nf + 4 * ((size_t)nm + 2) + nav + 4 * (size_t)e * n + n + 4 * 4 * 32 + 4 * 2 * 32 + 4 + 2
            + max_inner;
 }
 
