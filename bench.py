@@ -354,7 +354,10 @@ def main():
                                     "MEASURED_PEAKS.json has no FP64 figure",
                      "kernel": "solve_kernel", "kernel_ms": 1e3 * k_time, "algorithmic_gflop_per_launch": flops * 1e-9},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": hbm_ach / hbm_peak, "traffic": None,
+                         "frac": hbm_ach / hbm_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch at B = 1024
+                         # (ncu --set full, profiles/r01_solve_kernel_final_ncu_summary.txt); algorithmic: 10.9 MB
+                         "traffic": 13172480 if B == 1024 else None,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
     }
     if not args.no_extra:

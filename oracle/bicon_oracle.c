@@ -345,6 +345,9 @@ ALWAYS_INLINE double row_dot(const int FM, const int *rp, const int *cj, const d
 
 /* ------------------------------------------------------------------ problem data ------------ */
 
+static int g_f32_storage = 0;   /* study only (BICON_F32_STORAGE=1): ATA_ and A_ entries rounded to binary32 */
+void bicon_set_f32_storage(int on) { g_f32_storage = on; }
+
 /* ProblemData::set_data, [P]:31-39.  Q diagonal. */
 ALWAYS_INLINE void set_data(const int FM, const pattern *A, const double *Aval, double *Acsr,
                             const gram *G, double *H, double *h, double *w,
@@ -375,6 +378,10 @@ ALWAYS_INLINE void set_data(const int FM, const pattern *A, const double *Aval, 
             for (int r = s + 1; r < e; ++r) acc = MAD(FM, acc, two_rho * Aval[r], w[A->ri[r]]);
         }
         h[i] = acc + q[i];
+    }
+    if (g_f32_storage) {
+        for (int p = 0; p < G->nnz; ++p) H[p] = (double)(float)H[p];
+        for (int p = 0; p < A->nnz; ++p) Acsr[p] = (double)(float)Acsr[p];
     }
 }
 

@@ -90,6 +90,10 @@ void      bicon_ws_destroy(bicon_ws *ws);
 /* BiConvexMP::optimize (biconvex.cpp:80-120). Returns 0, or -1 on bad arguments. */
 int bicon_solve(bicon_ws *ws, const bicon_problem *p, const bicon_params *prm, bicon_result *out);
 
+/* Study hook (not part of the restatement): round the entries of ATA_ and A_ to binary32 after set_data, all
+ * arithmetic stays binary64 -- used to size a mixed-precision mode (DESIGN.md, FP32 note). */
+void bicon_set_f32_storage(int on);
+
 /* Host-side builders (biconvex.cpp:27-78). */
 void bicon_create_bound_constraints(int n_col, int n_eff, const double *cnt_plan,
                                     const double *b /* [n_col][6] */,
