@@ -92,3 +92,29 @@ def test_longer_horizons(oracle, gait, scale, n_expected):
     sol = BatchSolver(b.n_col, b.n_eff, max_batch=8).solve(b)
     ref = oracle.solve(b, n_threads=8)
     assert_same(sol, ref, f"{gait} n={n_expected}")
+
+
+def test_baseline_config1_full_batch_bit_for_bit(oracle):
+    """BASELINE config[1] at its full size: 1024 perturbed Solo12 trot states on one B200, every instance compared
+    with the oracle -- values, step sizes, iteration counters, status (the oracle needs a few seconds on the host cores)."""
+    _require_gpu()
+    import os
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.config(1, B=1024, seed=0)
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=1024).solve(b)
+    ref = oracle.solve(b, n_threads=max(1, len(os.sched_getaffinity(0))))
+    assert_same(sol, ref, "config1 B=1024")
+    assert (sol.status == 0).mean() > 0.8
+
+
+def test_bayesian_samples_batch(oracle):
+    """BASELINE config 5 shape: per-instance goals (vx, vy, w) and log-uniform scalings of W_X, W_F and rho."""
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.config(4, B=96, seed=5)
+    assert b.rho.shape == (96,) and b.W_F.shape[0] == 96
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=96).solve(b)
+    ref = oracle.solve(b, n_threads=8)
+    assert_same(sol, ref, "bayes")
