@@ -146,6 +146,30 @@ def other_workloads(device, arith):
                      "outer_mean": float(sol.iters[:, 0].mean()), "inner_mean": float(sol.iters[:, 1:3].sum(1).mean()),
                      "converged_frac": float((sol.status == 0).mean()), "nan_frac": float((sol.status == 2).mean())}
         s.close()
+    # f-1: only the centroidal states cross PCIe; contact plan and references are built on the device
+    from bunmpc_b200.motions import GAITS, ROBOTS
+    import torch
+    rb, gp = ROBOTS["solo12"], GAITS["solo12"]["trot"]
+    rng = np.random.default_rng(0)
+    B = 1024
+    com = np.array([0.0, 0.0, gp.nom_ht]) + rng.normal(0.0, 0.02, (B, 3))
+    vcom, amom = rng.normal(0.0, 0.1, (B, 3)), rng.normal(0.0, 0.02, (B, 3))
+    foot = np.broadcast_to(rb.foot_pos, (B, 4, 3)) + np.concatenate([rng.normal(0.0, 0.02, (B, 4, 2)), np.zeros((B, 4, 1))], 2)
+    t0s = rng.integers(0, 10, B) * gp.gait_dt
+    v_des = np.stack([rng.uniform(0.0, 0.3, B), np.zeros(B), np.zeros(B)], 1)
+    s = BatchSolver(gp.horizon(), 4, max_batch=B, device=device)
+
+    def run():
+        dev = s.build_device(rb, gp, com, vcom, amom, foot, t0s, v_des, np.zeros(B))
+        o = s.solve_resident(dev, arith=arith)
+        return o["F"].cpu(), o["X"].cpu(), o["status"].cpu()
+    run()
+    t0 = time.perf_counter()
+    run()
+    dt = time.perf_counter() - t0
+    out["solo12_trot_B1024_from_centroidal_states (device-side problem builder)"] = {
+        "solves_per_s_e2e": B / dt, "ms": 1e3 * dt, "h2d_bytes": int(B * 8 * (9 + 12 + 1 + 3 + 1 + 2))}
+    s.close()
     return out
 
 

@@ -42,6 +42,21 @@ class ExpandedProblem(C.Structure):
     _fields_ = [("batch", C.c_int)] + [(f, In) for f in EXPANDED_FIELDS]
 
 
+class Gait(C.Structure):
+    _fields_ = [("gait_period", C.c_double), ("gait_dt", C.c_double), ("gait_horizon", C.c_double),
+                ("stance_percent", C.c_double * 4), ("phase_offset", C.c_double * 4),
+                ("hip_offsets", (C.c_double * 2) * 4), ("foot_size", C.c_double), ("nom_ht", C.c_double),
+                ("ori_correction", C.c_double * 3), ("I_zz", C.c_double), ("W_X", C.c_double * 9),
+                ("W_X_ter", C.c_double * 9), ("W_F", C.c_double * 12), ("rho", C.c_double)]
+
+
+STATE_FIELDS = ("com", "vcom", "amom", "foot_pos", "t", "v_des", "w_des", "cs_yaw", "amom_des", "scales")
+
+
+class States(C.Structure):
+    _fields_ = [("batch", C.c_int)] + [(f, In) for f in STATE_FIELDS]
+
+
 class Solution(C.Structure):
     _fields_ = [("X", C.c_void_p), ("F", C.c_void_p), ("P", C.c_void_p), ("L", C.c_void_p), ("iters", C.c_void_p),
                 ("viol", C.c_void_p), ("status", C.c_void_p), ("viol_hist", C.c_void_p), ("cycles", C.c_void_p)]
@@ -50,7 +65,7 @@ class Solution(C.Structure):
 # every symbol include/bunmpc.h declares
 EXPORTS = ("bunmpc_version", "bunmpc_last_error", "bunmpc_default_params", "bunmpc_create", "bunmpc_destroy",
            "bunmpc_launch_count", "bunmpc_kernel_info", "bunmpc_expand_device", "bunmpc_solve_expanded_device",
-           "bunmpc_solve_compact_device", "bunmpc_solve_compact_host", "bunmpc_solve_expanded_host",
+           "bunmpc_solve_compact_device", "bunmpc_build_problem_device", "bunmpc_solve_compact_host", "bunmpc_solve_expanded_host",
            "bunmpc_centroidal_mats_host", "bunmpc_measure_fp64_peak", "bunmpc_selftest_division", "bunmpc_host_alloc", "bunmpc_host_free")
 
 _lib = None
@@ -83,6 +98,7 @@ def lib():
                                                C.POINTER(Solution), C.c_void_p]
     L.bunmpc_solve_compact_device.argtypes = [C.c_void_p, C.POINTER(CompactProblem), C.POINTER(Params),
                                               C.POINTER(Solution), C.c_void_p]
+    L.bunmpc_build_problem_device.argtypes = [C.c_void_p, C.POINTER(Gait), C.POINTER(States)] + [C.c_void_p] * 10
     L.bunmpc_solve_compact_host.argtypes = [C.c_void_p, C.POINTER(CompactProblem), C.POINTER(Params),
                                             C.POINTER(Solution)]
     L.bunmpc_solve_expanded_host.argtypes = [C.c_void_p, C.POINTER(ExpandedProblem), C.POINTER(Params),

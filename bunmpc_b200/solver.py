@@ -203,6 +203,78 @@ class BatchSolver:
                    cycles=torch.empty((B,), dtype=torch.int64, device=dev))
         return DeviceBatch(B=B, fields=fields, out=out, widths=w)
 
+    def build_device(self, robot, params, com, vcom, amom, foot_pos, t, v_des, w_des, yaw=0.0, amom_des=None,
+                     scales=None, L0=None) -> DeviceBatch:
+        """Batched problem builder ON THE DEVICE: contact plan (create_cnt_plan,
+        abstract_cyclic_gen.py:159-414) and nominal/terminal references (create_costs, :564-614) from centroidal
+        states; only the states cross PCIe.  Same results, bit for bit, as plan_builder.build_batch (numpy)."""
+        import torch
+        from .problem import L0_F, L0_X
+        dev = torch.device("cuda", self.device)
+        com = np.atleast_2d(np.asarray(com, dtype=np.float64))
+        B, n, e = com.shape[0], self.n_col, self.n_eff
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch}")
+        if params.horizon() != n:
+            raise ValueError("gait horizon does not match the solver")
+
+        def up(a, tail):
+            a = np.array(np.broadcast_to(np.asarray(a, dtype=np.float64), (B,) + tuple(tail)), order="C", copy=True)
+            return torch.from_numpy(a.reshape(B, -1)).to(dev)
+
+        yaw = np.broadcast_to(np.asarray(yaw, dtype=np.float64), (B,))
+        st_t = dict(com=up(com, (3,)), vcom=up(vcom, (3,)), amom=up(amom, (3,)), foot_pos=up(foot_pos, (e, 3)),
+                    t=up(t, ()), v_des=up(v_des, (3,)), w_des=up(w_des, ()),
+                    cs_yaw=up(np.stack([np.cos(yaw), np.sin(yaw)], axis=1), (2,)),
+                    amom_des=None if amom_des is None else up(amom_des, (3,)),
+                    scales=None if scales is None else up(scales, (3,)))
+        g = _lib.Gait()
+        g.gait_period, g.gait_dt, g.gait_horizon = params.gait_period, params.gait_dt, params.gait_horizon
+        for j in range(4):
+            g.stance_percent[j] = params.stance_percent[j]
+            g.phase_offset[j] = params.phase_offset[j]
+            g.hip_offsets[j][0], g.hip_offsets[j][1] = robot.hip_offsets[j][0], robot.hip_offsets[j][1]
+        g.foot_size, g.nom_ht, g.I_zz, g.rho = robot.foot_size, params.nom_ht, robot.I_zz, params.rho
+        for k in range(3):
+            g.ori_correction[k] = params.ori_correction[k]
+        for k in range(9):
+            g.W_X[k], g.W_X_ter[k] = params.W_X[k], params.W_X_ter[k]
+        for k in range(12):
+            g.W_F[k] = params.W_F[k]
+        st = _lib.States()
+        st.batch = B
+        widths = dict(com=3, vcom=3, amom=3, foot_pos=3 * e, t=1, v_des=3, w_des=1, cs_yaw=2, amom_des=3, scales=3)
+        for f in _lib.STATE_FIELDS:
+            tt = st_t[f]
+            setattr(st, f, _lib.In(None, 0) if tt is None else _lib.In(tt.data_ptr(), widths[f]))
+        f64 = dict(dtype=torch.float64, device=dev)
+        out = dict(x_init=torch.empty((B, 9), **f64), cnt_plan=torch.empty((B, n * e * 4), **f64),
+                   dt=torch.empty((B, n), **f64), X_nom=torch.empty((B, 9 * n), **f64), X_ter=torch.empty((B, 9), **f64))
+        if scales is not None:
+            out.update(W_X=torch.empty((B, 9 * n), **f64), W_X_ter=torch.empty((B, 9), **f64),
+                       W_F=torch.empty((B, self.nf), **f64), rho=torch.empty((B, 1), **f64))
+        ptr = lambda k: C.c_void_p(out[k].data_ptr()) if k in out else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().bunmpc_build_problem_device(
+            self._h, C.byref(g), C.byref(st), ptr("x_init"), ptr("cnt_plan"), ptr("dt"), ptr("X_nom"), ptr("X_ter"),
+            ptr("W_X"), ptr("W_X_ter"), ptr("W_F"), ptr("rho"), C.c_void_p(stream)), "bunmpc_build_problem_device")
+        one = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(1, -1))).to(dev)
+        fields = dict(out)
+        fields["m"] = one([robot.mass])
+        if scales is None:
+            fields.update(rho=one([params.rho]), W_X=one(np.tile(params.W_X, n)), W_X_ter=one(params.W_X_ter),
+                          W_F=one(np.tile(params.W_F, n)))
+        fields["bounds"] = one(np.tile([-robot.bx, -robot.by, 0, robot.bx, robot.by, robot.bz], n))
+        fields["L0"] = one([L0_F, L0_X]) if L0 is None else up(L0, (2,))
+        fields.update(X0=None, F0=None, P0=None)
+        res = dict(X=torch.empty((B, self.nx), **f64), F=torch.empty((B, self.nf), **f64),
+                   P=torch.empty((B, self.nx), **f64), L=torch.empty((B, 2), **f64),
+                   iters=torch.empty((B, 5), dtype=torch.int32, device=dev), viol=torch.empty((B,), **f64),
+                   status=torch.empty((B,), dtype=torch.int32, device=dev),
+                   cycles=torch.empty((B,), dtype=torch.int64, device=dev))
+        self._keep = st_t      # keep the state tensors alive until the (asynchronous) kernel has consumed them
+        return DeviceBatch(B=B, fields=fields, out=res, widths=self._widths())
+
     def solve_resident(self, dev: DeviceBatch, params: Optional[SolverParams] = None,
                        arith: int = _lib.ARITH_STRICT):
         """Expand + solve on device-resident inputs, asynchronous on torch's current stream."""

@@ -127,6 +127,40 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
 int bunmpc_solve_compact_device(bunmpc_solver *s, const bunmpc_compact_problem *p, const bunmpc_params *prm,
                                 const bunmpc_solution *out, void *stream);
 
+/* ---- batched problem builder on the device -------------------------------------------------
+ * What SoloMpcGaitGen does in python before it calls the solver -- create_cnt_plan
+ * (examples/mpc/abstract_cyclic_gen.py:159-414: Raibert contact plan, phase lookup of gait_planner.cpp:41-58,
+ * dt[0] rule) and the dynamics part of create_costs (:564-614: X_nom, X_ter) -- for a whole batch, starting
+ * from centroidal states (pinocchio stays on the caller's side). */
+typedef struct {
+    double gait_period, gait_dt, gait_horizon;   /* motions/cyclic/*.py */
+    double stance_percent[4], phase_offset[4];
+    double hip_offsets[4][2];                     /* abstract_cyclic_gen.py:51-69 (x, y) */
+    double foot_size;                             /* :31 */
+    double nom_ht;
+    double ori_correction[3];
+    double I_zz;                                  /* composite yaw inertia, used when w_des != 0 (:604) */
+    double W_X[9], W_X_ter[9], W_F[12], rho;      /* used only when per-instance scalings are given */
+} bunmpc_gait;
+
+typedef struct {
+    int batch;
+    bunmpc_in com, vcom, amom;     /* [B][3] each: X_init = [com, hg_lin/m, hg_ang] (:567-571) */
+    bunmpc_in foot_pos;            /* [B][4][3] current end-effector positions (rounded to 3 dp like :213) */
+    bunmpc_in t;                   /* [B] time inside the gait (replanning phase) */
+    bunmpc_in v_des;               /* [B][3] desired velocity, already in the local frame (:642-643) */
+    bunmpc_in w_des;               /* [B] */
+    bunmpc_in cs_yaw;              /* [B][2] cos and sin of the base yaw (R of :172-177) */
+    bunmpc_in amom_des;            /* [B][3] log3(R_des R_q^T) (:616-627); ptr NULL = 0 */
+    bunmpc_in scales;              /* [B][3] multipliers of (W_X and W_X_ter, W_F, rho); ptr NULL = none */
+} bunmpc_states;
+
+/* device pointers; writes x_init [B][9], cnt_plan [B][n][4][4], dt [B][n], X_nom [B][9n], X_ter [B][9] and, when
+ * st->scales.ptr != NULL, W_X [B][9n], W_X_ter [B][9], W_F [B][12n], rho [B] (otherwise those four may be NULL). */
+int bunmpc_build_problem_device(bunmpc_solver *s, const bunmpc_gait *g, const bunmpc_states *st, double *x_init,
+                                double *cnt_plan, double *dt, double *X_nom, double *X_ter, double *W_X,
+                                double *W_X_ter, double *W_F, double *rho, void *stream);
+
 /* ---- host-pointer entry points: copy in, solve, copy out, synchronise.  Pointers are host pointers
  *      (pinned memory makes the copies asynchronous).  This is what the python BiconvexMP calls. ---- */
 int bunmpc_solve_compact_host(bunmpc_solver *s, const bunmpc_compact_problem *p, const bunmpc_params *prm,

@@ -138,3 +138,39 @@ def test_errors_are_loud():
     s = BatchSolver(20, 4, max_batch=4)
     with pytest.raises(ValueError):
         s.solve(synthetic.perturbed(8, seed=0))         # batch > max_batch
+
+
+@pytest.mark.parametrize("gait,robot", [("trot", "solo12"), ("bound", "solo12"), ("jump", "solo12"), ("trot", "go2")])
+def test_device_problem_builder_matches_host_builder(gait, robot):
+    """the on-device batched builder (contact plan, X_nom, X_ter, scaled weights) against the numpy
+    restatement of the gait generator's rules, bit for bit, then solved from the device-resident problem."""
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.motions import GAITS, ROBOTS
+    from bunmpc_b200.plan_builder import build_batch
+    from bunmpc_b200.solver import BatchSolver
+    rb, gp = ROBOTS[robot], GAITS[robot][gait]
+    rng = np.random.default_rng(3)
+    B = 257
+    com = np.array([0.0, 0.0, gp.nom_ht]) + rng.normal(0, 0.02, (B, 3))
+    vcom, amom = rng.normal(0, 0.1, (B, 3)), rng.normal(0, 0.02, (B, 3))
+    foot = np.broadcast_to(rb.foot_pos, (B, 4, 3)) + rng.normal(0, 0.02, (B, 4, 3))
+    t = rng.uniform(0, gp.gait_period, B).round(3)
+    v_des = np.stack([rng.uniform(0, 0.3, B), rng.uniform(-0.1, 0.1, B), np.zeros(B)], 1)
+    w_des = np.where(rng.uniform(size=B) < 0.5, 0.0, rng.uniform(-0.1, 0.1, B))
+    yaw = rng.uniform(-0.3, 0.3, B)
+    amom_des = rng.normal(0, 0.05, (B, 3))
+    sc = np.exp(rng.uniform(np.log(0.5), np.log(2.0), (B, 3)))
+    host = build_batch(rb, gp, com, vcom, amom, foot, t, v_des, w_des, yaw=yaw, amom_des=amom_des,
+                       scale_W_X=sc[:, 0], scale_W_F=sc[:, 1], scale_rho=sc[:, 2])
+    s = BatchSolver(host.n_col, host.n_eff, max_batch=B)
+    dev = s.build_device(rb, gp, com, vcom, amom, foot, t, v_des, w_des, yaw=yaw, amom_des=amom_des, scales=sc)
+    for f in ("x_init", "cnt_plan", "dt", "X_nom", "X_ter", "W_X", "W_X_ter", "W_F", "rho"):
+        got = dev.fields[f].cpu().numpy().reshape(getattr(host, f).shape)
+        assert np.array_equal(got, getattr(host, f)), f
+    out = s.solve_resident(dev)
+    import torch
+    torch.cuda.synchronize()
+    ref = s.solve(host)
+    assert np.array_equal(out["iters"].cpu().numpy(), ref.iters)
+    Fd = out["F"].cpu().numpy()
+    assert ((Fd == ref.F) | (np.isnan(Fd) & np.isnan(ref.F))).all()
