@@ -245,11 +245,23 @@ def main():
         gathered = [torch.empty((world * B, solver.nf), dtype=torch.float64, device="cuda"),
                     torch.empty((world * B, solver.nx), dtype=torch.float64, device="cuda")]
 
+    stats = torch.zeros(17, dtype=torch.float64, device="cuda")
+
     def step_resident():
         out = solver.solve_resident(dev, arith=arith)
         if world > 1:
+            # the path's only exchange steps (BASELINE.json): gather the solved trajectories and all-reduce the
+            # sufficient statistics of the Bayesian goal update (goal = desired velocity, error proxy = ||viol||)
             dist.all_gather_into_tensor(gathered[0], out["F"])
             dist.all_gather_into_tensor(gathered[1], out["X"])
+            g = dev.fields["X_ter"][:, 3:6]
+            e = torch.nan_to_num(out["viol"], nan=0.0)
+            stats[0] = float(g.shape[0])
+            stats[1:4] = g.sum(0)
+            stats[4:13] = (g[:, :, None] * g[:, None, :]).sum(0).reshape(9)
+            stats[13] = e.sum()
+            stats[14:17] = (e[:, None] * g).sum(0)
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         return out
 
     def barrier():
@@ -362,7 +374,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "instances_per_gpu_per_step": B, "n_col": batch.n_col, "n_eff": batch.n_eff,
                    "arith": args.arith, "l2": "flushed between steps (256 MiB write)",
-                   "sharding": "independent instances per rank, seed=rank" + (", nccl all_gather of F,X per step" if world > 1 else ""),
+                   "sharding": "independent instances per rank, seed=rank" + (", nccl all_gather of F,X and all_reduce of 17 posterior statistics per step" if world > 1 else ""),
                    "kernel": info},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
