@@ -174,3 +174,25 @@ def test_device_problem_builder_matches_host_builder(gait, robot):
     assert np.array_equal(out["iters"].cpu().numpy(), ref.iters)
     Fd = out["F"].cpu().numpy()
     assert ((Fd == ref.F) | (np.isnan(Fd) & np.isnan(ref.F))).all()
+
+
+def test_gait_generator_shim_replans(oracle):
+    """CyclicQuadrupedGaitGen (alias SoloMpcGaitGen): two consecutive replans from centroidal states; the FISTA step
+    sizes persist across replans like the KinoDynMP's solver objects (simulation.py:408)."""
+    from bunmpc_b200 import CyclicQuadrupedGaitGen
+    from bunmpc_b200.motions import SOLO12, solo12_trot
+    gg = CyclicQuadrupedGaitGen(None, None, None, planning_time=0.05)
+    gg.update_gait_params(solo12_trot, 0.0)
+    com, foot = np.array([0.01, -0.02, 0.21]), SOLO12.foot_pos
+    L_prev = None
+    for t in (0.0, 0.05):
+        com_int, mom_int, f_int = gg.optimize_centroidal(com, [0.05, 0.0, 0.0], np.zeros(3), foot, t, np.array([0.2, 0.0, 0.0]), 0.0)
+        batch, sol = gg.last
+        ref = oracle.solve(batch)
+        assert np.array_equal(sol.F, ref["F"]) and np.array_equal(sol.iters, ref["iters"])
+        if L_prev is not None:
+            assert np.array_equal(batch.L0, L_prev)
+        L_prev = sol.L
+        steps = sum(int(d / 0.001) for d in batch.dt[0][: gg.size])
+        assert com_int.shape == (steps, 3) and mom_int.shape == (steps, 6) and f_int.shape == (steps, 12)
+        assert np.array_equal(f_int[0], sol.F[0][:12])

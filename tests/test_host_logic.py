@@ -110,3 +110,19 @@ def test_posterior_update_helpers():
     assert np.isclose(post.sum(), 1.0) and np.unravel_index(post.argmax(), post.shape)[0] in (6, 7)
     st = dist.goal_sufficient_stats(np.ones((5, 3)), np.arange(5.0))
     assert st.shape == (17,) and st[0] == 5 and st[13] == 10.0
+
+
+def test_gait_gen_shim_sizes_and_interpolation():
+    """update_gait_params sizes (abstract_cyclic_gen.py:125-153) and the 1 kHz interpolation (:677-692)."""
+    import bunmpc_b200 as pkg
+    from bunmpc_b200.motions import solo12_trot
+    assert pkg.SoloMpcGaitGen is pkg.CyclicQuadrupedGaitGen is pkg.AbstractGaitGen
+    gg = pkg.CyclicQuadrupedGaitGen(None, None, None, planning_time=0.05)
+    gg.update_gait_params(solo12_trot, 0.0)
+    assert gg.horizon == 20 and gg.ik_horizon == 10 and gg.size == 3      # min(10, int(0.05/0.05)+2) = 3
+    knots = np.arange(12.0).reshape(4, 3)
+    out = gg.interpolate(knots, np.array([0.03, 0.05, 0.05, 0.05]), 3)
+    assert out.shape == (30 + 50 + 50, 3)
+    assert np.array_equal(out[0], knots[0]) and np.array_equal(out[29], knots[1]) and np.array_equal(out[30], knots[1])
+    with pytest.raises(ImportError):
+        gg.optimize(np.zeros(19), np.zeros(18), 0.0, np.array([0.2, 0, 0]), 0.0)
