@@ -96,6 +96,7 @@ static solve_fn pick_kernel2(int n, int nthreads, bool comb)
     }
     if (n == 20 && nthreads <= 480) return solve_kernel<NE, ARITH, 20, false, 480, 128>;   // BASELINE trot horizon
     if (nthreads <= 512) return solve_kernel<NE, ARITH, 0, false, 512, 128>;
+    if (nthreads <= 640) return solve_kernel<NE, ARITH, 0, false, 640, 96>;     // 5 warps per scheduler
     if (nthreads <= 768) return solve_kernel<NE, ARITH, 0, false, 768, 80>;
     return solve_kernel<NE, ARITH, 0, false, 1024, 64>;
 }
