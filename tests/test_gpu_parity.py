@@ -94,6 +94,22 @@ def test_longer_horizons(oracle, gait, scale, n_expected):
     assert_same(sol, ref, f"{gait} n={n_expected}")
 
 
+@pytest.mark.parametrize("gait,n_expected", [("bound", 48), ("jump", 60)])
+def test_longer_horizons_with_rejections(oracle, gait, n_expected):
+    """Combined-role kernels (n = 48, 60) with tiny initial step sizes: the line-search test needs the
+    |A y + b|^2 partials of the row work in the one-barrier pipeline as well as in the sequential replay."""
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.perturbed(6, "solo12", gait, seed=23, horizon_scale=2.0)
+    assert b.n_col == n_expected
+    b.L0 = np.array([[1.0, 40.0]])
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=8).solve(b)
+    ref = oracle.solve(b, n_threads=8)
+    assert ref["iters"][:, 3].min() > 5 and ref["iters"][:, 4].min() > 5
+    assert_same(sol, ref, f"{gait} n={n_expected} with rejections")
+
+
 def test_baseline_config1_full_batch_bit_for_bit(oracle):
     """BASELINE config[1] at its full size: 1024 perturbed Solo12 trot states on one B200, every instance compared
     with the oracle -- values, step sizes, iteration counters, status (the oracle needs a few seconds on the host cores)."""
