@@ -50,7 +50,6 @@ struct bunmpc_solver {
     long long launches = 0;
     int nthreads = 0, smem_bytes = 0, nav = 0;
     bool comb = false;               // combined warp roles (long horizons)
-    int variant = 1;                 // 1: one variable per thread, rows in registers; 2: two per thread; 3: rows in shared memory
     int ctas_per_sm[2] = {0, 0};     // per arith
 };
 
@@ -89,17 +88,12 @@ typedef void (*solve_fn)(const SolveArgs);
 // lets two CTAs share an SM (the register file is split over 4 schedulers of 16K registers each)
 // split roles: threads = 32 (variable warps + row warps + 1); combined roles (long horizons): 32 (variable warps + 1)
 template <int NE, int ARITH>
-static solve_fn pick_kernel2(int n, int nthreads, bool comb, int variant)
+static solve_fn pick_kernel2(int n, int nthreads, bool comb)
 {
     if (comb) {
         if (nthreads <= 768) return solve_kernel<NE, ARITH, 0, true, 768, 80>;
         return solve_kernel<NE, ARITH, 0, true, 1024, 64>;
     }
-    if (n == 20 && variant == 2) return solve_kernel<NE, ARITH, 20, false, 256, 128, 2>;   // two variables per thread, two CTAs per SM
-    if (n == 20 && variant == 5) return solve_kernel<NE, ARITH, 20, false, 256, 128, 2, true>;
-    if (n == 20 && variant == 6) return solve_kernel<NE, ARITH, 20, false, 256, 96, 2, true>;
-    if (n == 20 && variant == 4) return solve_kernel<NE, ARITH, 20, false, 256, 80, 2, true>;   // both: three CTAs per SM
-    if (n == 20 && variant == 3) return solve_kernel<NE, ARITH, 20, false, 480, 64, 1, true>;   // rows in shared memory, two CTAs per SM
     if (n == 20 && nthreads <= 480) return solve_kernel<NE, ARITH, 20, false, 480, 128>;   // BASELINE trot horizon
     if (nthreads <= 512) return solve_kernel<NE, ARITH, 0, false, 512, 128>;
     if (nthreads <= 640) return solve_kernel<NE, ARITH, 0, false, 640, 96>;     // 5 warps per scheduler
@@ -107,20 +101,18 @@ static solve_fn pick_kernel2(int n, int nthreads, bool comb, int variant)
     return solve_kernel<NE, ARITH, 0, false, 1024, 64>;
 }
 
-static solve_fn pick(int e, int arith, int n, int nthreads, bool comb, int variant)
+static solve_fn pick(int e, int arith, int n, int nthreads, bool comb)
 {
-    if (e == 4) return arith ? pick_kernel2<4, 1>(n, nthreads, comb, variant) : pick_kernel2<4, 0>(n, nthreads, comb, variant);
+    if (e == 4) return arith ? pick_kernel2<4, 1>(n, nthreads, comb) : pick_kernel2<4, 0>(n, nthreads, comb);
     return nullptr;
 }
 
 // must mirror the carve-up at the top of solve_kernel
-static size_t smem_doubles(int n, int e, int max_inner, int nav, int variant)
+static size_t smem_doubles(int n, int e, int max_inner, int nav)
 {
     int nx = 9 * (n + 1), nf = 3 * e * n, nm = nx > nf ? nx : nf;
-    size_t d = (size_t)nx * 4 + nf + 4 * ((size_t)nm + 2) + nav + 4 * (size_t)e * n + n + 4 * 4 * 32 + 4 * 2 * 32 + 4 + 2
-               + max_inner;
-    if (variant >= 3) d += 3 * (size_t)e * nm + 2 * (size_t)e * nx;   // Hessian and constraint rows in shared memory
-    return d;
+    return (size_t)nx * 4 + nf + 4 * ((size_t)nm + 2) + nav + 4 * (size_t)e * n + n + 4 * 4 * 32 + 4 * 2 * 32 + 4 + 2
+           + max_inner;
 }
 
 extern "C" {
@@ -152,17 +144,13 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     const int wf = (nf + 29) / 30, wx = (nx + 31) / 32;
     const int nvw = wf > wx ? wf : wx;
     const bool comb = nvw + wx + 1 > 32;                   // too many warps for split roles: combine them
-    int nthreads = 32 * (comb ? nvw + 1 : nvw + wx + 1);   // variable warps (+ row warps) + the scalar warp
-    const char *var_env = getenv("BUNMPC_VARIANT");
-    const int variant = (n == 20 && var_env) ? atoi(var_env) : 1;
-    if (variant == 2 || variant >= 4) nthreads = 32 * ((nvw + 1) / 2 + (wx + 1) / 2 + 1);
+    const int nthreads = 32 * (comb ? nvw + 1 : nvw + wx + 1);   // variable warps (+ row warps) + the scalar warp
     if (nthreads > 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: n_col too large for one CTA per instance");
     CK(cudaSetDevice(device));
     bunmpc_solver *s = new bunmpc_solver();
     s->device = device; s->n = n; s->e = e; s->nx = nx; s->nf = nf; s->max_batch = max_batch;
     s->nthreads = nthreads;
     s->comb = comb;
-    s->variant = variant;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     s->num_sms = prop.multiProcessorCount;
@@ -211,9 +199,9 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     CK(cudaMalloc(&s->mats, sizeof(double) * ((size_t)nx * nf + (size_t)nx * nx + 2 * (size_t)nx + 4 * (size_t)e * n + n + nx + nf + 9)));
 
     // opt in to the shared memory the kernel needs and record occupancy
-    s->smem_bytes = (int)(smem_doubles(n, e, 150, s->nav, s->variant) * sizeof(double));
+    s->smem_bytes = (int)(smem_doubles(n, e, 150, s->nav) * sizeof(double));
     for (int arith = 0; arith < 2; ++arith) {
-        solve_fn fn = pick(e, arith, n, nthreads, comb, s->variant);
+        solve_fn fn = pick(e, arith, n, nthreads, comb);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, nthreads, s->smem_bytes));
@@ -307,9 +295,9 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     a.max_outer = prm->max_outer; a.max_inner = prm->max_inner;
     a.tol = prm->tol; a.exit_tol = prm->exit_tol; a.beta = prm->beta; a.mu = prm->mu;
     a.coef = s->coef; a.TF = s->TF.d; a.TX = s->TX.d; a.work_counter = s->work_counter; a.nav = s->nav;
-    const int smem = (int)(smem_doubles(s->n, s->e, prm->max_inner, s->nav, s->variant) * sizeof(double));
+    const int smem = (int)(smem_doubles(s->n, s->e, prm->max_inner, s->nav) * sizeof(double));
     if (smem > 200 * 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: shared memory need exceeds 200 KB");
-    solve_fn fn = pick(s->e, prm->arith, s->n, s->nthreads, s->comb, s->variant);
+    solve_fn fn = pick(s->e, prm->arith, s->n, s->nthreads, s->comb);
     int per_sm = s->ctas_per_sm[prm->arith];
     if (smem != s->smem_bytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->nthreads, smem));
     if (per_sm < 1) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: kernel does not fit on an SM");
