@@ -36,7 +36,9 @@ struct bunmpc_solver {
     int device = 0, n = 0, e = 0, nx = 0, nf = 0, max_batch = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
     DevTables TF, TX;
-    unsigned int *work_counter = nullptr;
+    unsigned int *work_counter = nullptr;   // [3]: next item, finished instances, queue tail
+    int *queue = nullptr; double *sl_d = nullptr; int *sl_i = nullptr; long long *sl_c = nullptr;   // time slicing
+    int slice_env = -1;              // BUNMPC_SLICE: outer iterations per slice (0 = off), -1 = automatic
     double *coef = nullptr;          // device, [coef_len]
     int coef_len = 0;
     // staging (device), sized for max_batch
@@ -135,6 +137,7 @@ void *bunmpc_host_alloc(unsigned long long bytes)
 void bunmpc_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 static const int kMaxInnerTable = 4096;
+static const int kQueuePerInstance = 16;   // an instance is parked at most 15 times per solve
 
 int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max_batch)
 {
@@ -184,7 +187,12 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
         CK(cudaMemcpy(s->coef, c.data(), sizeof(double) * kMaxInnerTable, cudaMemcpyHostToDevice));
         s->coef_len = kMaxInnerTable;
     }
-    CK(cudaMalloc(&s->work_counter, sizeof(unsigned int)));
+    CK(cudaMalloc(&s->work_counter, 3 * sizeof(unsigned int)));
+    CK(cudaMalloc(&s->queue, sizeof(int) * kQueuePerInstance * (size_t)max_batch));
+    CK(cudaMalloc(&s->sl_d, sizeof(double) * (size_t)max_batch * (2 * (size_t)nx + nf + 2)));
+    CK(cudaMalloc(&s->sl_i, sizeof(int) * 8 * (size_t)max_batch));
+    CK(cudaMalloc(&s->sl_c, sizeof(long long) * (size_t)max_batch));
+    if (const char *ev = getenv("BUNMPC_SLICE")) s->slice_env = atoi(ev);
 
     // staging buffers
     const size_t B = (size_t)max_batch;
@@ -217,6 +225,7 @@ void bunmpc_destroy(bunmpc_solver *s)
     cudaSetDevice(s->device);
     for (void *p : s->TF.allocs) cudaFree(p);
     for (void *p : s->TX.allocs) cudaFree(p);
+    cudaFree(s->queue); cudaFree(s->sl_d); cudaFree(s->sl_i); cudaFree(s->sl_c);
     cudaFree(s->work_counter); cudaFree(s->coef); cudaFree(s->st_in); cudaFree(s->ex);
     cudaFree(s->out_d); cudaFree(s->out_i); cudaFree(s->out_c); cudaFree(s->mats);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -303,7 +312,18 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     if (per_sm < 1) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: kernel does not fit on an SM");
     long long grid = (long long)s->num_sms * per_sm;
     if (grid > a.B) grid = a.B;
-    CK(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), st));
+    // time slicing: with more instances than resident CTAs, park an instance after a few outer iterations so that
+    // the launch ends on a short slice instead of on the longest instance (iteration counts spread 4x)
+    int slice = 0;
+    if (a.B > grid) {
+        const int min_slice = (prm->max_outer + kQueuePerInstance - 1) / kQueuePerInstance;   // <= 15 parks per instance
+        slice = s->slice_env >= 0 ? s->slice_env : 8;
+        if (slice > 0 && slice < min_slice) slice = min_slice;
+    }
+    a.slice_outer = slice; a.queue_cap = kQueuePerInstance * a.B;
+    a.queue = s->queue; a.sl_d = s->sl_d; a.sl_i = s->sl_i; a.sl_c = s->sl_c;
+    CK(cudaMemsetAsync(s->work_counter, 0, 3 * sizeof(unsigned int), st));
+    if (slice > 0) CK(cudaMemsetAsync(s->queue, 0xff, sizeof(int) * (size_t)a.queue_cap, st));
     fn<<<(unsigned)grid, s->nthreads, smem, st>>>(a);
     s->launches++;
     CK(cudaGetLastError());

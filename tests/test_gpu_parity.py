@@ -110,6 +110,26 @@ def test_longer_horizons_with_rejections(oracle, gait, n_expected):
     assert_same(sol, ref, f"{gait} n={n_expected} with rejections")
 
 
+def test_time_sliced_instances(oracle):
+    """More instances than resident CTAs: the kernel parks an instance every few outer iterations and resumes it
+    later, possibly on another SM.  Results, counters and the violation history must not notice."""
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.perturbed(333, "solo12", "trot", seed=5)
+    s = BatchSolver(b.n_col, b.n_eff, max_batch=333)
+    assert 333 > s.kernel_info()["num_sms"] * s.kernel_info()["ctas_per_sm"]
+    sol = s.solve(b, viol_hist=True)
+    ref = oracle.solve(b, n_threads=16)
+    assert_same(sol, ref, "time-sliced")
+    assert sol.iters[:, 0].max() > 16                       # some instances were parked at least twice
+    for i in (0, 100, 332):                                 # history: one entry per outer iteration, NaN after the exit
+        k = sol.iters[i, 0]
+        assert np.isfinite(sol.viol_hist[i, :k]).all() and np.isnan(sol.viol_hist[i, k:]).all()
+        assert sol.viol_hist[i, k - 1] == sol.viol[i]
+    assert (sol.cycles > 0).all()
+
+
 def test_baseline_config1_full_batch_bit_for_bit(oracle):
     """BASELINE config[1] at its full size: 1024 perturbed Solo12 trot states on one B200, every instance compared
     with the oracle -- values, step sizes, iteration counters, status (the oracle needs a few seconds on the host cores)."""
