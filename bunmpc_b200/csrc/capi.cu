@@ -97,6 +97,8 @@ static solve_fn pick_kernel2(int n, int nthreads, bool comb)
         return solve_kernel<NE, ARITH, 0, true, 1024, 64>;
     }
     if (n == 20 && nthreads <= 480) return solve_kernel<NE, ARITH, 20, false, 480, 128>;   // BASELINE trot horizon
+    if (n == 24 && nthreads <= 640) return solve_kernel<NE, ARITH, 24, false, 640, 96>;    // bound gait horizon (solo12_bound.py)
+    if (n == 30 && nthreads <= 768) return solve_kernel<NE, ARITH, 30, false, 768, 80>;    // jump gait horizon (solo12_jump.py)
     if (nthreads <= 512) return solve_kernel<NE, ARITH, 0, false, 512, 128>;
     if (nthreads <= 640) return solve_kernel<NE, ARITH, 0, false, 640, 96>;     // 5 warps per scheduler
     if (nthreads <= 768) return solve_kernel<NE, ARITH, 0, false, 768, 80>;

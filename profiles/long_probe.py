@@ -3,8 +3,9 @@ import sys, time, numpy as np
 sys.path.insert(0, '.')
 from bunmpc_b200 import synthetic
 from bunmpc_b200.solver import BatchSolver
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 2.0
 for gait, B in (("trot", 592), ("bound", 592), ("jump", 592)):
-    b = synthetic.perturbed(B, "solo12", gait, seed=0, horizon_scale=2.0)
+    b = synthetic.perturbed(B, "solo12", gait, seed=0, horizon_scale=scale)
     s = BatchSolver(b.n_col, b.n_eff, max_batch=B)
     s.solve(b); t = time.perf_counter(); sol = s.solve(b); dt = time.perf_counter() - t
     it = sol.iters[:, 1] + sol.iters[:, 2]
