@@ -3,6 +3,7 @@
 // fails the entry point returns BUNMPC_ERR_CUDA and bunmpc_last_error() says why.
 #include "../../include/bunmpc.h"
 #include "kernels.cuh"
+#include "solve_inst.hpp"
 #include "tables.hpp"
 
 #include <cmath>
@@ -83,32 +84,13 @@ static cudaError_t upload_tables(DevTables &D, const HostTables &H)
     return cudaSuccess;
 }
 
-// ---- kernel dispatch: thread-count classes with their own register budgets ----
-typedef void (*solve_fn)(const SolveArgs);
-
-// thread-count classes: threads = 32 (variable warps + row warps + 1 scalar warp); the register cap is what
-// lets two CTAs share an SM (the register file is split over 4 schedulers of 16K registers each)
-// split roles: threads = 32 (variable warps + row warps + 1); combined roles (long horizons): 32 (variable warps + 1)
-template <int NE, int ARITH>
-static solve_fn pick_kernel2(int n, int nthreads, bool comb)
-{
-    if (comb) {
-        if (nthreads <= 768) return solve_kernel<NE, ARITH, 0, true, 768, 80>;
-        return solve_kernel<NE, ARITH, 0, true, 1024, 64>;
-    }
-    if (n == 20 && nthreads <= 480) return solve_kernel<NE, ARITH, 20, false, 480, 128>;   // BASELINE trot horizon
-    if (n == 24 && nthreads <= 640) return solve_kernel<NE, ARITH, 24, false, 640, 96>;    // bound gait horizon (solo12_bound.py)
-    if (n == 30 && nthreads <= 768) return solve_kernel<NE, ARITH, 30, false, 768, 80>;    // jump gait horizon (solo12_jump.py)
-    if (nthreads <= 512) return solve_kernel<NE, ARITH, 0, false, 512, 128>;
-    if (nthreads <= 640) return solve_kernel<NE, ARITH, 0, false, 640, 96>;     // 5 warps per scheduler
-    if (nthreads <= 768) return solve_kernel<NE, ARITH, 0, false, 768, 80>;
-    return solve_kernel<NE, ARITH, 0, false, 1024, 64>;
-}
-
+// ---- kernel dispatch: the instantiations live in solve_inst.cu (one translation unit per group) ----
 static solve_fn pick(int e, int arith, int n, int nthreads, bool comb)
 {
-    if (e == 4) return arith ? pick_kernel2<4, 1>(n, nthreads, comb) : pick_kernel2<4, 0>(n, nthreads, comb);
-    return nullptr;
+    if (e != 4) return nullptr;
+    if (comb) return arith ? solve_inst_2_1(n, nthreads) : solve_inst_2_0(n, nthreads);
+    if (solve_fn f = arith ? solve_inst_0_1(n, nthreads) : solve_inst_0_0(n, nthreads)) return f;
+    return arith ? solve_inst_1_1(n, nthreads) : solve_inst_1_0(n, nthreads);
 }
 
 // must mirror the carve-up at the top of solve_kernel
