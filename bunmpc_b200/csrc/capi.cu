@@ -88,8 +88,9 @@ static cudaError_t upload_tables(DevTables &D, const HostTables &H)
 static solve_fn pick(int e, int arith, int n, int nthreads, bool comb)
 {
     if (e != 4) return nullptr;
-    if (comb) return arith ? solve_inst_2_1(n, nthreads) : solve_inst_2_0(n, nthreads);
     if (solve_fn f = arith ? solve_inst_0_1(n, nthreads) : solve_inst_0_0(n, nthreads)) return f;
+    if (solve_fn f = arith ? solve_inst_3_1(n, nthreads) : solve_inst_3_0(n, nthreads)) return f;
+    if (comb) return arith ? solve_inst_2_1(n, nthreads) : solve_inst_2_0(n, nthreads);
     return arith ? solve_inst_1_1(n, nthreads) : solve_inst_1_0(n, nthreads);
 }
 

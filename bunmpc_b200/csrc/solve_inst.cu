@@ -5,7 +5,7 @@
 #include "solve_inst.hpp"
 
 #ifndef INST_GROUP
-#error "compile with -DINST_GROUP=0|1|2 -DINST_ARITH=0|1"
+#error "compile with -DINST_GROUP=0|1|2|3 -DINST_ARITH=0|1"
 #endif
 #define INST_CAT2(a, b, c) a##b##_##c
 #define INST_CAT(a, b, c) INST_CAT2(a, b, c)
@@ -20,6 +20,12 @@ solve_fn INST_NAME(int n, int nthreads)
     if (n == 20 && nthreads <= 480) return solve_kernel<NE, ARITH, 20, false, 480, 128>;   // BASELINE trot horizon
     if (n == 24 && nthreads <= 640) return solve_kernel<NE, ARITH, 24, false, 640, 96>;    // bound gait horizon (solo12_bound.py)
     if (n == 30 && nthreads <= 768) return solve_kernel<NE, ARITH, 30, false, 768, 80>;    // jump gait horizon (solo12_jump.py)
+    return nullptr;
+#elif INST_GROUP == 3
+    // doubled horizons of the three gaits (analysis/solve_times_test.py:60-66); 48 and 60 run with combined roles
+    if (n == 40 && nthreads <= 1024) return solve_kernel<NE, ARITH, 40, false, 1024, 64>;
+    if (n == 48 && nthreads <= 768) return solve_kernel<NE, ARITH, 48, true, 768, 80>;
+    if (n == 60 && nthreads <= 1024) return solve_kernel<NE, ARITH, 60, true, 1024, 64>;
     return nullptr;
 #elif INST_GROUP == 1
     (void)n;
