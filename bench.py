@@ -170,6 +170,17 @@ def other_workloads(device, arith):
     out["solo12_trot_B1024_from_centroidal_states (device-side problem builder)"] = {
         "solves_per_s_e2e": B / dt, "ms": 1e3 * dt, "h2d_bytes": int(B * 8 * (9 + 12 + 1 + 3 + 1 + 2))}
     s.close()
+    # f-3: lock-step rollouts, one batched solve per replanning tick, step sizes carried, host-side plan builder and plant
+    from bunmpc_b200.rollout import EpisodeState, LockstepRollouts, TrackingPlant
+    st = EpisodeState(com, vcom, amom, np.array(foot), t0s.astype(np.float64), np.zeros(B))
+    roll = LockstepRollouts(rb, gp, plant=TrackingPlant(0.002, 0.02, 0.0, seed=1), device=device)
+    roll.run(st, v_des, 0.0, n_ticks=1)
+    t0 = time.perf_counter()
+    rec = roll.run(st, v_des, 0.0, n_ticks=6)
+    dt = time.perf_counter() - t0
+    out["lockstep_rollouts_B1024_6_ticks (host plan builder + plant in the loop)"] = {
+        "solves_per_s_e2e": int((np.array([(r > 0).any(1).sum() for r in rec.iters])).sum()) / dt, "ms": 1e3 * dt,
+        "failed": int((rec.failed_at >= 0).sum())}
     return out
 
 
