@@ -22,7 +22,7 @@ ip = C.POINTER(C.c_int)
 
 class Params(C.Structure):
     _fields_ = [("max_outer", C.c_int), ("max_inner", C.c_int), ("tol", C.c_double), ("exit_tol", C.c_double),
-                ("beta", C.c_double), ("mu", C.c_double), ("arith", C.c_int)]
+                ("beta", C.c_double), ("mu", C.c_double), ("arith", C.c_int), ("slice_outer", C.c_int)]
 
 
 class In(C.Structure):

@@ -111,6 +111,7 @@ void bunmpc_default_params(bunmpc_params *p)
 {
     p->max_outer = 100; p->max_inner = 150; p->tol = 1e-5; p->exit_tol = 1e-3; p->beta = 1.5; p->mu = 1.0;
     p->arith = BUNMPC_ARITH_STRICT;
+    p->slice_outer = 0;
 }
 
 void *bunmpc_host_alloc(unsigned long long bytes)
@@ -302,7 +303,7 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     int slice = 0;
     if (a.B > grid) {
         const int min_slice = (prm->max_outer + kQueuePerInstance - 1) / kQueuePerInstance;   // <= 15 parks per instance
-        slice = s->slice_env >= 0 ? s->slice_env : 8;
+        slice = prm->slice_outer < 0 ? 0 : (prm->slice_outer > 0 ? prm->slice_outer : (s->slice_env >= 0 ? s->slice_env : 8));
         if (slice > 0 && slice < min_slice) slice = min_slice;
     }
     a.slice_outer = slice; a.queue_cap = kQueuePerInstance * a.B;

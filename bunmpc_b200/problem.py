@@ -33,6 +33,7 @@ class SolverParams:
     exit_tol: float = 1e-3    # biconvex.hpp:160
     beta: float = 1.5         # fista.hpp:54
     mu: float = 1.0           # fista.hpp:60
+    slice_outer: int = 0      # scheduling only (time slicing): 0 automatic, <0 off, >0 outer iterations per slice
 
 
 def _arr(a, tail, name):

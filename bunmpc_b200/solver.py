@@ -20,7 +20,7 @@ from .problem import BatchSolution, CentroidalBatch, SolverParams
 def _c_params(prm: Optional[SolverParams], arith: int) -> _lib.Params:
     prm = prm or SolverParams()
     return _lib.Params(int(prm.max_outer), int(prm.max_inner), float(prm.tol), float(prm.exit_tol),
-                       float(prm.beta), float(prm.mu), int(arith))
+                       float(prm.beta), float(prm.mu), int(arith), int(prm.slice_outer))
 
 
 def _in_np(a: Optional[np.ndarray], width: int) -> _lib.In:

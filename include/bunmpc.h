@@ -47,6 +47,9 @@ typedef struct {
     double beta;        /* 1.5 */
     double mu;          /* 1.0 */
     int    arith;       /* BUNMPC_ARITH_* */
+    int    slice_outer; /* scheduling only, results never depend on it: outer iterations an instance runs before it is
+                         * parked and re-queued (time slicing).  0 = automatic (8 when the batch exceeds the resident
+                         * CTAs, else off), < 0 = off */
 } bunmpc_params;
 
 typedef struct {

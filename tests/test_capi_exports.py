@@ -29,7 +29,7 @@ def test_version_and_defaults_without_gpu():
     assert L.bunmpc_version() == 100
     p = _lib.Params()
     L.bunmpc_default_params(ctypes.byref(p))
-    assert (p.max_outer, p.max_inner, p.tol, p.exit_tol, p.beta, p.mu, p.arith) == (100, 150, 1e-5, 1e-3, 1.5, 1.0, 0)
+    assert (p.max_outer, p.max_inner, p.tol, p.exit_tol, p.beta, p.mu, p.arith, p.slice_outer) == (100, 150, 1e-5, 1e-3, 1.5, 1.0, 0, 0)
 
 
 def test_product_code_never_touches_the_oracle():

@@ -130,6 +130,21 @@ def test_time_sliced_instances(oracle):
     assert (sol.cycles > 0).all()
 
 
+@pytest.mark.parametrize("slice_outer", [1, 3, -1])
+def test_slice_length_never_changes_results(oracle, slice_outer):
+    """Parking after every single outer iteration (up to 11 parks per instance), every third, or never."""
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.problem import SolverParams
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.perturbed(300, "solo12", "trot", seed=31)
+    prm = SolverParams(max_outer=12, slice_outer=slice_outer)
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=300).solve(b, prm, viol_hist=True)
+    ref = oracle.solve(b, oracle.default_params(max_outer=12), n_threads=16)
+    assert_same(sol, ref, f"slice_outer={slice_outer}")
+    assert np.isfinite(sol.viol_hist[np.arange(300), sol.iters[:, 0] - 1]).all()
+
+
 def test_baseline_config1_full_batch_bit_for_bit(oracle):
     """BASELINE config[1] at its full size: 1024 perturbed Solo12 trot states on one B200, every instance compared
     with the oracle -- values, step sizes, iteration counters, status (the oracle needs a few seconds on the host cores)."""
