@@ -123,6 +123,19 @@ def run_cpu(batch, cores, max_instances, budget_s=25.0):
     return n / dt, n, dt
 
 
+def smem_roofline(iters, k_time, clocks, info):
+    wf_per_iter = 572.0
+    mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
+    if not mhz or not k_time:
+        return None
+    wf = wf_per_iter * float(iters[:, 1].sum() + iters[:, 2].sum())
+    ach = wf / (k_time * mhz * 1e6 * info["num_sms"])
+    return {"bound": "shared-memory data pipe", "achieved": ach, "peak": 1.0, "unit": "wavefronts/clk/SM", "frac": ach,
+            "peak_source": "nominal 1 wavefront (128 B) per clock per SM",
+            "wavefronts_per_inner_iteration": wf_per_iter,
+            "ncu_pct_of_peak_sustained_elapsed": 57.8}   # l1tex__data_pipe_lsu_wavefronts_mem_shared, profiled launch
+
+
 def other_workloads(device, arith):
     """Short single-GPU runs of the other BASELINE.json configs (per-GPU shard sizes), host-buffer path, one warm-up
     + one timed solve each: reported for context, not part of `value`."""
@@ -400,10 +413,14 @@ def main():
                      "peak_source": "DFMA micro-benchmark measured in this run (bunmpc_measure_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 figure",
                      "kernel": "solve_kernel", "kernel_ms": 1e3 * k_time, "algorithmic_gflop_per_launch": flops * 1e-9},
+        # the busiest pipe (ncu): shared-memory data stage.  572 wavefronts per inner iteration (403 without bank
+        # conflicts) is the ncu count of the profiled launch of this same workload (profiles/r01_solve_kernel_s2_
+        # ncu_summary.txt: 57.8 % of peak); scaled here by the live iteration counters and the live kernel time.
+        "roofline_smem": smem_roofline(iters, k_time, clocks, info),
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_ach / hbm_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch at B = 1024
-                         # (ncu --set full, profiles/r01_solve_kernel_final_ncu_summary.txt); algorithmic: 10.9 MB
+                         # (ncu --set full, profiles/r01_solve_kernel_final_ncu_summary.txt; 13.3 MB in r01_solve_kernel_s2_ncu_summary.txt); algorithmic: 10.9 MB
                          "traffic": 13172480 if B == 1024 else None,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
     }
