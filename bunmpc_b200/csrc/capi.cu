@@ -39,7 +39,6 @@ struct bunmpc_solver {
     DevTables TF, TX;
     unsigned int *work_counter = nullptr;   // [3]: next item, finished instances, queue tail
     int *queue = nullptr; double *sl_d = nullptr; int *sl_i = nullptr; long long *sl_c = nullptr;   // time slicing
-    int slice_env = -1;              // BUNMPC_SLICE: outer iterations per slice (0 = off), -1 = automatic
     double *coef = nullptr;          // device, [coef_len]
     int coef_len = 0;
     // staging (device), sized for max_batch
@@ -178,7 +177,6 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     CK(cudaMalloc(&s->sl_d, sizeof(double) * (size_t)max_batch * (2 * (size_t)nx + nf + 2)));
     CK(cudaMalloc(&s->sl_i, sizeof(int) * 8 * (size_t)max_batch));
     CK(cudaMalloc(&s->sl_c, sizeof(long long) * (size_t)max_batch));
-    if (const char *ev = getenv("BUNMPC_SLICE")) s->slice_env = atoi(ev);
 
     // staging buffers
     const size_t B = (size_t)max_batch;
@@ -303,7 +301,7 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     int slice = 0;
     if (a.B > grid) {
         const int min_slice = (prm->max_outer + kQueuePerInstance - 1) / kQueuePerInstance;   // <= 15 parks per instance
-        slice = prm->slice_outer < 0 ? 0 : (prm->slice_outer > 0 ? prm->slice_outer : (s->slice_env >= 0 ? s->slice_env : 8));
+        slice = prm->slice_outer < 0 ? 0 : (prm->slice_outer > 0 ? prm->slice_outer : 8);
         if (slice > 0 && slice < min_slice) slice = min_slice;
     }
     a.slice_outer = slice; a.queue_cap = kQueuePerInstance * a.B;
