@@ -1,0 +1,60 @@
+"""Randomised GPU-vs-oracle soak: random gaits, robots, horizons, batch sizes, iteration caps, tolerances, initial step
+sizes (forcing line-search rejections), arithmetic modes and slice lengths; every result must be bit-identical.
+    python profiles/soak_parity.py [seconds] [seed]          (GPU box only; the oracle is the checker)"""
+import sys, time
+import numpy as np
+sys.path.insert(0, '.')
+from oracle import oracle
+from bunmpc_b200 import synthetic
+from bunmpc_b200._lib import ARITH_FMA, ARITH_STRICT
+from bunmpc_b200.problem import SolverParams
+from bunmpc_b200.solver import BatchSolver
+
+oracle.build()
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+t_end = time.time() + budget
+n_cases = n_inst = n_bad = 0
+solvers = {}
+while time.time() < t_end:
+    gait = rng.choice(["trot", "bound", "jump"])
+    robot = rng.choice(["solo12", "solo12", "go2"])
+    scale = float(rng.choice([0.5, 1.0, 1.0, 1.5, 2.0]))
+    B = int(rng.choice([1, 7, 33, 150, 300, 600]))
+    bseed = int(rng.integers(1 << 30))
+    b = synthetic.perturbed(B, robot, gait, seed=bseed, horizon_scale=scale,
+                            vy_range=(-0.1, 0.1), w_range=(-0.1, 0.1))
+    prm = SolverParams(max_outer=int(rng.choice([3, 10, 25, 100])), max_inner=int(rng.choice([1, 2, 3, 4, 5, 9, 40, 150])),
+                       tol=float(rng.choice([1e-5, 1e-3, 1e-1])), slice_outer=int(rng.choice([0, 0, 1, 3, -1])))
+    if prm.slice_outer > 0 and prm.max_outer > 16 * prm.slice_outer:
+        prm.slice_outer = 0
+    if rng.random() < 0.3:
+        b.L0 = np.array([[float(10 ** rng.uniform(-1, 2.7)), float(10 ** rng.uniform(1, 6.3))]])
+    if rng.random() < 0.2:
+        nx, nf = 9 * (b.n_col + 1), 12 * b.n_col
+        b.X0, b.F0, b.P0 = rng.normal(0, 0.1, (B, nx)), rng.normal(0, 1.0, (B, nf)), rng.normal(0, 1e-3, (B, nx))
+    fma = rng.random() < 0.25
+    key = (b.n_col, 600)
+    if key not in solvers:
+        solvers[key] = BatchSolver(b.n_col, 4, max_batch=600)
+    sol = solvers[key].solve(b, prm, arith=ARITH_FMA if fma else ARITH_STRICT)
+    ref = oracle.solve(b, oracle.default_params(max_outer=prm.max_outer, max_inner=prm.max_inner, tol=prm.tol,
+                                                use_fma=1 if fma else 0), n_threads=32)
+    ok = np.array_equal(sol.iters, ref["iters"]) and np.array_equal(sol.status, ref["status"])
+    detail = []
+    if not ok:
+        bad_i = np.flatnonzero((sol.iters != ref["iters"]).any(1) | (sol.status != ref["status"]))
+        detail.append(f"iters/status differ in {len(bad_i)} instances, first {bad_i[:3]}: gpu {sol.iters[bad_i[:2]].tolist()} {sol.status[bad_i[:2]].tolist()} ref {ref['iters'][bad_i[:2]].tolist()} {ref['status'][bad_i[:2]].tolist()}")
+    for k in ("F", "X", "P", "L", "viol"):
+        a, r = getattr(sol, k), ref[k]
+        same = (a == r) | (np.isnan(a) & np.isnan(r))
+        if not same.all():
+            ok = False
+            rows = np.flatnonzero(~same.reshape(same.shape[0], -1).all(1))
+            detail.append(f"{k}: {len(rows)} instances, first {rows[:3]}, gpu nan {np.isnan(a[rows[0]]).any()} ref nan {np.isnan(r[rows[0]]).any()}")
+    n_cases += 1; n_inst += B
+    if not ok:
+        n_bad += 1
+        print("MISMATCH", gait, robot, scale, B, "seed", bseed, prm, "fma" if fma else "strict", "L0", b.L0.tolist(), "warm", b.X0 is not None, "|", " ; ".join(detail), flush=True)
+print(f"soak: {n_cases} cases, {n_inst} instances, {n_bad} mismatching cases")
+sys.exit(1 if n_bad else 0)

@@ -115,3 +115,18 @@ def test_plan_without_contacts_and_nan_inputs(oracle):
     assert_same(sol, ref, "no contacts / NaN")
     assert sol.status[3] == 2 and sol.iters[3, 0] == 1 and np.isnan(sol.F[3]).any()
     assert (sol.F[0] == 0).all()
+
+
+def test_step_size_overflows_to_infinity(oracle):
+    """A diverging line search (Go2 mass, one inner iteration per solve) rejects ~1740 steps: L = L0 * 1.5^k overflows
+    to +inf, after which gradient / L is exactly 0 in the reference.  Found by profiles/soak_parity.py."""
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    from bunmpc_b200.problem import SolverParams
+    b = synthetic.perturbed(600, "go2", "jump", seed=756643367, vy_range=(-0.1, 0.1), w_range=(-0.1, 0.1)).select(np.arange(160, 176))
+    b.L0 = np.array([[138.5017783022929, 341.3416382669748]])
+    prm = SolverParams(max_outer=100, max_inner=1, tol=1e-3)
+    sol = BatchSolver(b.n_col, 4, max_batch=16).solve(b, prm)
+    ref = oracle.solve(b, oracle.default_params(max_outer=100, max_inner=1, tol=1e-3), n_threads=16)
+    assert np.isinf(ref["L"]).any() and ref["iters"][:, 3].max() > 1700
+    assert_same(sol, ref, "L overflow")
