@@ -130,3 +130,14 @@ def test_step_size_overflows_to_infinity(oracle):
     ref = oracle.solve(b, oracle.default_params(max_outer=100, max_inner=1, tol=1e-3), n_threads=16)
     assert np.isinf(ref["L"]).any() and ref["iters"][:, 3].max() > 1700
     assert_same(sol, ref, "L overflow")
+
+
+def test_randomised_soak_short():
+    """Ten seconds of profiles/soak_parity.py: random gaits, robots, horizons 1..77, batch sizes, iteration caps,
+    tolerances, beta/mu, initial step sizes, warm starts, arithmetic modes, slice lengths -- all bit-identical."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "profiles", "soak_parity.py"), "10", "123"], cwd=root,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "0 mismatching cases" in r.stdout
