@@ -144,6 +144,8 @@ def other_workloads(device, arith):
     out = {}
     cases = [("config2_go2_trot_B2048_n20 (16384/8 GPUs)", lambda: synthetic.config(2, B=2048)),
              ("config3_go2_bound_B512_n48 (reference algorithm diverges: cone quirk Q2, see DESIGN.md 6)", lambda: synthetic.config(3, B=512)),
+             ("solo12_bound_B1024_n24 (bound gait, its own horizon)", lambda: synthetic.perturbed(1024, "solo12", "bound", seed=0)),
+             ("solo12_jump_B1024_n30 (jump gait, its own horizon)", lambda: synthetic.perturbed(1024, "solo12", "jump", seed=0)),
              ("solo12_bound_B1024_n48 (config 3 gait and horizon, Solo12 mass)", lambda: synthetic.perturbed(1024, "solo12", "bound", seed=0, horizon_scale=2.0)),
              ("solo12_jump_B512_n60", lambda: synthetic.perturbed(512, "solo12", "jump", seed=0, horizon_scale=2.0)),
              ("config4_bayes_goal+weight_samples_B8192_n20 (65536/8 GPUs)", lambda: synthetic.config(4, B=8192)),

@@ -28,7 +28,12 @@ def _worker(rank, world, port, q):
 
     sol = bdist.solve_sharded(batch, solve_fn)
     stats = bdist.allreduce_stats(bdist.goal_sufficient_stats(np.full((rank + 1, 3), rank + 1.0), np.ones(rank + 1)))
-    q.put((rank, sol.X, sol.iters, stats))
+    # f-3: every rank folds the goals of ITS episodes into the grid posterior; one all-reduce of the log-likelihood grid
+    from bunmpc_b200.rollout import GoalPosterior
+    post = GoalPosterior(n=12)
+    goals = np.array([[0.05, 0.0, 0.0], [0.1, 0.02, -0.02], [0.2, -0.05, 0.03], [0.25, 0.05, 0.0]])
+    post.update_batch(goals[bdist.shard_indices(4, rank, world)], all_reduce=True)
+    q.put((rank, sol.X, sol.iters, stats, post.p))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -48,6 +53,10 @@ def test_sharded_solve_gathers_full_batch():
         p.join(timeout=60)
         assert p.exitcode == 0
     full = oracle.solve(synthetic.perturbed(5, seed=0), params=oracle.default_params(max_outer=3, max_inner=20))
-    for rank, X, iters, stats in res:
+    from bunmpc_b200.rollout import GoalPosterior
+    one = GoalPosterior(n=12)
+    one.update_batch(np.array([[0.05, 0.0, 0.0], [0.1, 0.02, -0.02], [0.2, -0.05, 0.03], [0.25, 0.05, 0.0]]))
+    for rank, X, iters, stats, post in res:
         assert np.array_equal(X, full["X"]) and np.array_equal(iters, full["iters"])
         assert stats[0] == 3 and np.allclose(stats[1:4], 1 * 1.0 + 2 * 2.0)
+        assert np.allclose(post, one.p, rtol=1e-12)          # sharded posterior == single-process posterior
