@@ -17,3 +17,17 @@ def test_fp64_peak_is_sane():
     from bunmpc_b200.solver import BatchSolver
     tf = BatchSolver(20, 4, max_batch=1).measure_fp64_peak()
     assert 20.0 < tf < 60.0, tf
+
+
+def test_cycles_per_inner_iteration_budget():
+    """Performance guard (a one-line change in the division helper once cost 35 % without failing any parity test):
+    the n = 20 kernel spends ~1230 SM cycles per FISTA iteration (in-kernel clock64 per instance)."""
+    import numpy as np
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    b = synthetic.config(1, B=148, seed=0)
+    s = BatchSolver(b.n_col, b.n_eff, max_batch=148)
+    s.solve(b)
+    sol = s.solve(b)
+    cpi = (sol.cycles / (sol.iters[:, 1] + sol.iters[:, 2])).mean()
+    assert cpi < 1400, f"{cpi:.0f} cycles per inner iteration (expected ~1230)"
