@@ -411,7 +411,10 @@ def main():
                        "inner_x_mean": float(iters[:, 2].mean()), "inner_total_max": int((iters[:, 1] + iters[:, 2]).max()),
                        "converged_frac": float((out["status"] == 0).mean())},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                     "frac": achieved / fp64_peak if fp64_peak else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch of this workload
+                     # (ncu --set full, profiles/r01_solve_kernel_s2_ncu_summary.txt); algorithmic: 10.9 MB
+                     "traffic": 13452544 if B == 1024 else None,
                      "peak_source": "DFMA micro-benchmark measured in this run (bunmpc_measure_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 figure",
                      "kernel": "solve_kernel", "kernel_ms": 1e3 * k_time, "algorithmic_gflop_per_launch": flops * 1e-9},
@@ -421,9 +424,7 @@ def main():
         "roofline_smem": smem_roofline(iters, k_time, clocks, info),
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_ach / hbm_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch at B = 1024
-                         # (ncu --set full, profiles/r01_solve_kernel_final_ncu_summary.txt; 13.3 MB in r01_solve_kernel_s2_ncu_summary.txt); algorithmic: 10.9 MB
-                         "traffic": 13172480 if B == 1024 else None,
+                         "traffic": 13452544 if B == 1024 else None,   # same ncu capture as roofline.traffic
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
     }
     if not args.no_extra:
