@@ -1,7 +1,7 @@
 """Randomised GPU-vs-oracle soak: random gaits, robots, horizons, batch sizes, iteration caps, tolerances, initial step
 sizes (forcing line-search rejections), arithmetic modes and slice lengths; every result must be bit-identical.
     python profiles/soak_parity.py [seconds] [seed]          (GPU box only; the oracle is the checker)"""
-import sys, time
+import os, sys, time
 import numpy as np
 sys.path.insert(0, '.')
 from oracle import oracle
@@ -27,6 +27,7 @@ def truncate_or_tile(b, n):
 
 
 oracle.build()
+BATCHES = [int(x) for x in os.environ.get("SOAK_BATCHES", "1,7,33,150,300,600").split(",")]
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 t_end = time.time() + budget
@@ -36,7 +37,7 @@ while time.time() < t_end:
     gait = rng.choice(["trot", "bound", "jump"])
     robot = rng.choice(["solo12", "solo12", "go2"])
     scale = float(rng.choice([0.5, 1.0, 1.0, 1.5, 2.0]))
-    B = int(rng.choice([1, 7, 33, 150, 300, 600]))
+    B = int(rng.choice(BATCHES))
     bseed = int(rng.integers(1 << 30))
     b = synthetic.perturbed(B, robot, gait, seed=bseed, horizon_scale=scale,
                             vy_range=(-0.1, 0.1), w_range=(-0.1, 0.1),
@@ -59,9 +60,9 @@ while time.time() < t_end:
         nx, nf = 9 * (b.n_col + 1), 12 * b.n_col
         b.X0, b.F0, b.P0 = rng.normal(0, 0.1, (B, nx)), rng.normal(0, 1.0, (B, nf)), rng.normal(0, 1e-3, (B, nx))
     fma = rng.random() < 0.25
-    key = (b.n_col, 600)
+    key = (b.n_col, max(BATCHES))
     if key not in solvers:
-        solvers[key] = BatchSolver(b.n_col, 4, max_batch=600)
+        solvers[key] = BatchSolver(b.n_col, 4, max_batch=max(BATCHES))
     sol = solvers[key].solve(b, prm, arith=ARITH_FMA if fma else ARITH_STRICT)
     ref = oracle.solve(b, oracle.default_params(max_outer=prm.max_outer, max_inner=prm.max_inner, tol=prm.tol,
                                                 exit_tol=prm.exit_tol, beta=prm.beta, mu=prm.mu,
