@@ -427,9 +427,10 @@ def main():
                          "traffic": 13452544 if B == 1024 else None,   # same ncu capture as roofline.traffic
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
     }
-    if not args.no_extra:
+    # context legs run on rank 0 of a single-GPU run only (the other ranks of a multi-GPU run would just wait)
+    if not args.no_extra and world == 1:
         line["other_workloads"] = other_workloads(local_rank, arith)
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         cores = cpu_cores()
         v, n, dt = run_cpu(synthetic.config(1, B=B, seed=0), cores, B, budget_s=25.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
