@@ -1,5 +1,5 @@
 """Per-source-line instruction counts of one kernel from an ncu report (source page) and the line table of the
-   cubin that was profiled:  python profiles/per_line.py <report.ncu-rep> <libbunmpc.so> <mangled kernel name> [N_iter]
+   cubin that was profiled:  python profiles/per_line.py <report.ncu-rep> <object or library holding ONE cubin with the kernel, e.g. bunmpc_b200/csrc/obj/inst_0_0.o> <mangled kernel name> [N_iter]
    Prints warp-instructions per source line (divided by N_iter if given), with the opcode mix of each line."""
 import collections
 import csv
@@ -15,7 +15,8 @@ def line_table(so, kernel):
     import os
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, capture_output=True)
     import glob
-    sass = subprocess.run(["nvdisasm", "-g", "-c"] + glob.glob(d + "/*.cubin"), capture_output=True, text=True).stdout
+    sass = "".join(subprocess.run(["nvdisasm", "-g", "-c", f], capture_output=True, text=True).stdout
+                   for f in sorted(glob.glob(d + "/*.cubin")))
     tab, cur, inside = {}, None, False
     for ln in sass.splitlines():
         if ln.startswith(".text."):
