@@ -4,7 +4,6 @@
 #include "../../include/bunmpc.h"
 #include "kernels.cuh"
 #include "solve_inst.hpp"
-#include "tables.hpp"
 
 #include <cmath>
 #include <cstdio>
@@ -28,15 +27,9 @@ static thread_local std::string g_err;
 
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
-struct DevTables {
-    TablesDev d{};
-    std::vector<void *> allocs;
-};
-
 struct bunmpc_solver {
     int device = 0, n = 0, e = 0, nx = 0, nf = 0, max_batch = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
-    DevTables TF, TX;
     unsigned int *work_counter = nullptr;   // [3]: next item, finished instances, queue tail
     int *queue = nullptr; double *sl_d = nullptr; int *sl_i = nullptr; long long *sl_c = nullptr;   // time slicing
     double *coef = nullptr;          // device, [coef_len]
@@ -49,57 +42,40 @@ struct bunmpc_solver {
     int *out_i = nullptr;            // iters, status
     long long *out_c = nullptr;      // cycles
     double *mats = nullptr;          // scratch for bunmpc_centroidal_mats_host
+    double *hist = nullptr;          // [max_batch][hist_cols] viol_hist staging of the host entry points (grown on demand)
+    int hist_cols = 0;
     long long launches = 0;
-    int nthreads = 0, smem_bytes = 0, nav = 0;
-    bool comb = false;               // combined warp roles (long horizons)
+    int nthreads = 0, smem_bytes = 0;
     int ctas_per_sm[2] = {0, 0};     // per arith
 };
 
-template <class T>
-static cudaError_t upload(DevTables &D, const std::vector<T> &h, const T **dst)
+static size_t smem_bytes_for(int n, int e, int max_inner, int nthreads)
 {
-    void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, h.size() * sizeof(T) + 16);
-    if (e != cudaSuccess) return e;
-    D.allocs.push_back(p);
-    *dst = reinterpret_cast<const T *>(p);
-    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return (size_t)make_layout(n, e, max_inner, nthreads / 32).total * sizeof(double);
 }
 
-static cudaError_t upload_tables(DevTables &D, const HostTables &H)
+static const int kMaxSmemBytes = 227 * 1024 - 64;   // dynamic + the kernel's 16 static bytes must fit the 227 KB opt-in limit
+
+static void free_solver(bunmpc_solver *s)
 {
-    cudaError_t e;
-    D.d.nv = H.nv; D.d.nr = H.nr; D.d.nvp = H.nvp; D.d.nrp = H.nrp;
-    if ((e = upload(D, H.h_len, &D.d.h_len)) != cudaSuccess) return e;
-    if ((e = upload(D, H.h_np, &D.d.h_np)) != cudaSuccess) return e;
-    if ((e = upload(D, H.c_len, &D.d.c_len)) != cudaSuccess) return e;
-    if ((e = upload(D, H.a_len, &D.d.a_len)) != cudaSuccess) return e;
-    if ((e = upload(D, H.h_col, &D.d.h_col)) != cudaSuccess) return e;
-    if ((e = upload(D, H.c_row, &D.d.c_row)) != cudaSuccess) return e;
-    if ((e = upload(D, H.c_aidx, &D.d.c_aidx)) != cudaSuccess) return e;
-    if ((e = upload(D, H.a_col, &D.d.a_col)) != cudaSuccess) return e;
-    if ((e = upload(D, H.a_aidx, &D.d.a_aidx)) != cudaSuccess) return e;
-    if ((e = upload(D, H.h_pair, &D.d.h_pair)) != cudaSuccess) return e;
-    return cudaSuccess;
+    if (!s) return;
+    cudaFree(s->queue); cudaFree(s->sl_d); cudaFree(s->sl_i); cudaFree(s->sl_c);
+    cudaFree(s->work_counter); cudaFree(s->coef); cudaFree(s->st_in); cudaFree(s->ex);
+    cudaFree(s->out_d); cudaFree(s->out_i); cudaFree(s->out_c); cudaFree(s->mats); cudaFree(s->hist);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
 }
 
-// ---- kernel dispatch: the instantiations live in solve_inst.cu (one translation unit per group) ----
-static solve_fn pick(int e, int arith, int n, int nthreads, bool comb)
-{
-    if (e != 4) return nullptr;
-    if (solve_fn f = arith ? solve_inst_0_1(n, nthreads) : solve_inst_0_0(n, nthreads)) return f;
-    if (solve_fn f = arith ? solve_inst_3_1(n, nthreads) : solve_inst_3_0(n, nthreads)) return f;
-    if (comb) return arith ? solve_inst_2_1(n, nthreads) : solve_inst_2_0(n, nthreads);
-    return arith ? solve_inst_1_1(n, nthreads) : solve_inst_1_0(n, nthreads);
-}
-
-// must mirror the carve-up at the top of solve_kernel
-static size_t smem_doubles(int n, int e, int max_inner, int nav)
-{
-    int nx = 9 * (n + 1), nf = 3 * e * n, nm = nx > nf ? nx : nf;
-    return (size_t)nx * 4 + nf + 4 * ((size_t)nm + 2) + nav + 4 * (size_t)e * n + n + 4 * 4 * 32 + 4 * 2 * 32 + 4 + 2
-           + max_inner;
-}
+// like CK, but releases a half-built solver first
+#define CKS(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            free_solver(s);                                                                        \
+            return BUNMPC_ERR_CUDA;                                                                \
+        }                                                                                          \
+    } while (0)
 
 extern "C" {
 
@@ -129,33 +105,18 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     if (!out || n_col < 1 || max_batch < 1) return fail(BUNMPC_ERR_ARG, "bunmpc_create: bad argument");
     if (n_eff != 4) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: kernels are built for n_eff == 4");
     const int n = n_col, e = n_eff, nx = 9 * (n + 1), nf = 3 * e * n;
-    const int wf = (nf + 29) / 30, wx = (nx + 31) / 32;
-    const int nvw = wf > wx ? wf : wx;
-    const bool comb = nvw + wx + 1 > 32;                   // too many warps for split roles: combine them
-    const int nthreads = 32 * (comb ? nvw + 1 : nvw + wx + 1);   // variable warps (+ row warps) + the scalar warp
-    if (nthreads > 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: n_col too large for one CTA per instance");
+    const int nthreads = solve_threads(n, e);             // e*n force threads / 3(n+1) state threads, one CTA per instance
+    if (nthreads == 0) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: n_col too large for one CTA per instance");
+    if (smem_bytes_for(n, e, 150, nthreads) > (size_t)kMaxSmemBytes)
+        return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: n_col too large for the shared memory of one SM");
     CK(cudaSetDevice(device));
     bunmpc_solver *s = new bunmpc_solver();
     s->device = device; s->n = n; s->e = e; s->nx = nx; s->nf = nf; s->max_batch = max_batch;
     s->nthreads = nthreads;
-    s->comb = comb;
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
+    CKS(cudaGetDeviceProperties(&prop, device));
     s->num_sms = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-
-    // symbolic tables
-    const int nav0 = (9 * e * n > 27 * n + 9) ? 9 * e * n : 27 * n + 9;   // value index nav0 and iterate slot nm hold 0
-    const int nm0 = nx > nf ? nx : nf;
-    HostTables hf = build_tables(pattern_Ax(n, e), nx, nf, 9 * e * n, 3 * e, 3, 2 * e, 3, nav0, nm0);
-    HostTables hx = build_tables(pattern_Af(n), nx, nx, 27 * n + 9, 11, 4, 4, 4, nav0, nm0);
-    if (!hf.contiguous_rows || hf.KH > 3 * e || hf.PM > 3 || hf.KA > 2 * e || hf.KC > 3 || hx.KH > 11 || hx.PM > 4 || hx.KA > 4 || hx.KC > 4) {
-        delete s;
-        return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: sparsity pattern exceeds the kernel's table bounds");
-    }
-    CK(upload_tables(s->TF, hf));
-    CK(upload_tables(s->TX, hx));
-    s->nav = nav0 + 2;   // + the always-zero element the padded table entries point at
+    CKS(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 
     // FISTA momentum coefficients (t_k - 1)/t_{k+1} with t_{k+1} = 1 + sqrt(1 + 4 t_k^2)/2 (fista.cpp:34-35, sic);
     // the sequence does not depend on the data, so it is tabulated once (IEEE sqrt and / are exact on both sides).
@@ -168,35 +129,36 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
             c[i] = (t_k - 1) / t_k_1;
             t_k = t_k_1;
         }
-        CK(cudaMalloc(&s->coef, sizeof(double) * kMaxInnerTable));
-        CK(cudaMemcpy(s->coef, c.data(), sizeof(double) * kMaxInnerTable, cudaMemcpyHostToDevice));
+        CKS(cudaMalloc(&s->coef, sizeof(double) * kMaxInnerTable));
+        CKS(cudaMemcpy(s->coef, c.data(), sizeof(double) * kMaxInnerTable, cudaMemcpyHostToDevice));
         s->coef_len = kMaxInnerTable;
     }
-    CK(cudaMalloc(&s->work_counter, 3 * sizeof(unsigned int)));
-    CK(cudaMalloc(&s->queue, sizeof(int) * kQueuePerInstance * (size_t)max_batch));
-    CK(cudaMalloc(&s->sl_d, sizeof(double) * (size_t)max_batch * (2 * (size_t)nx + nf + 2)));
-    CK(cudaMalloc(&s->sl_i, sizeof(int) * 8 * (size_t)max_batch));
-    CK(cudaMalloc(&s->sl_c, sizeof(long long) * (size_t)max_batch));
+    CKS(cudaMalloc(&s->work_counter, 3 * sizeof(unsigned int)));
+    CKS(cudaMalloc(&s->queue, sizeof(int) * kQueuePerInstance * (size_t)max_batch));
+    CKS(cudaMalloc(&s->sl_d, sizeof(double) * (size_t)max_batch * (2 * (size_t)nx + nf + 2)));
+    CKS(cudaMalloc(&s->sl_i, sizeof(int) * 8 * (size_t)max_batch));
+    CKS(cudaMalloc(&s->sl_c, sizeof(long long) * (size_t)max_batch));
 
     // staging buffers
     const size_t B = (size_t)max_batch;
     const size_t in_doubles = B * (2 + 9 + 4 * (size_t)e * n + n + 2 + 2 * (size_t)nx + nf     // m,rho,x_init,cnt,dt,L0,X0,P0,F0
                                    + 4 * (size_t)nx + 2 * (size_t)nf + 6 * (size_t)n + 18) + 64;  // costs/bounds in either form
     s->st_in_doubles = in_doubles;
-    CK(cudaMalloc(&s->st_in, sizeof(double) * in_doubles));
-    CK(cudaMalloc(&s->ex, sizeof(double) * B * (4 * (size_t)nx + 2 * (size_t)nf)));
-    CK(cudaMalloc(&s->out_d, sizeof(double) * B * (2 * (size_t)nx + nf + 3)));
-    CK(cudaMalloc(&s->out_i, sizeof(int) * B * 6));
-    CK(cudaMalloc(&s->out_c, sizeof(long long) * B));
-    CK(cudaMalloc(&s->mats, sizeof(double) * ((size_t)nx * nf + (size_t)nx * nx + 2 * (size_t)nx + 4 * (size_t)e * n + n + nx + nf + 9)));
+    CKS(cudaMalloc(&s->st_in, sizeof(double) * in_doubles));
+    CKS(cudaMalloc(&s->ex, sizeof(double) * B * (4 * (size_t)nx + 2 * (size_t)nf)));
+    CKS(cudaMalloc(&s->out_d, sizeof(double) * B * (2 * (size_t)nx + nf + 3)));
+    CKS(cudaMalloc(&s->out_i, sizeof(int) * B * 6));
+    CKS(cudaMalloc(&s->out_c, sizeof(long long) * B));
+    CKS(cudaMalloc(&s->mats, sizeof(double) * ((size_t)nx * nf + (size_t)nx * nx + 2 * (size_t)nx + 4 * (size_t)e * n + n + nx + nf + 9)));
 
     // opt in to the shared memory the kernel needs and record occupancy
-    s->smem_bytes = (int)(smem_doubles(n, e, 150, s->nav) * sizeof(double));
+    s->smem_bytes = (int)smem_bytes_for(n, e, 150, nthreads);
     for (int arith = 0; arith < 2; ++arith) {
-        solve_fn fn = pick(e, arith, n, nthreads, comb);
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        solve_fn fn = solve_pick(nthreads, arith);
+        CKS(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+        CKS(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, nthreads, s->smem_bytes));
+        CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, nthreads, s->smem_bytes));
         s->ctas_per_sm[arith] = nb;
     }
     *out = s;
@@ -207,13 +169,7 @@ void bunmpc_destroy(bunmpc_solver *s)
 {
     if (!s) return;
     cudaSetDevice(s->device);
-    for (void *p : s->TF.allocs) cudaFree(p);
-    for (void *p : s->TX.allocs) cudaFree(p);
-    cudaFree(s->queue); cudaFree(s->sl_d); cudaFree(s->sl_i); cudaFree(s->sl_c);
-    cudaFree(s->work_counter); cudaFree(s->coef); cudaFree(s->st_in); cudaFree(s->ex);
-    cudaFree(s->out_d); cudaFree(s->out_i); cudaFree(s->out_c); cudaFree(s->mats);
-    if (s->stream) cudaStreamDestroy(s->stream);
-    delete s;
+    free_solver(s);
 }
 
 long long bunmpc_launch_count(const bunmpc_solver *s) { return s ? s->launches : 0; }
@@ -237,6 +193,10 @@ static int check_params(const bunmpc_solver *s, const bunmpc_params *prm)
         return fail(BUNMPC_ERR_ARG, "max_inner/max_outer out of range");
     if (prm->arith != BUNMPC_ARITH_STRICT && prm->arith != BUNMPC_ARITH_FMA)
         return fail(BUNMPC_ERR_UNSUPPORTED, "unknown arith mode");
+    // a rejected step multiplies L by beta until it is accepted (fista.cpp:19): beta <= 1 would spin forever inside a
+    // persistent kernel; the tolerances only have to be comparable
+    if (!(prm->beta > 1.0) || !std::isfinite(prm->beta)) return fail(BUNMPC_ERR_ARG, "beta must be finite and > 1");
+    if (std::isnan(prm->tol) || std::isnan(prm->exit_tol) || std::isnan(prm->mu)) return fail(BUNMPC_ERR_ARG, "tol / exit_tol / mu is NaN");
     return BUNMPC_OK;
 }
 
@@ -268,29 +228,26 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     if (!s || !p || !out) return fail(BUNMPC_ERR_ARG, "solve: null argument");
     int rc = check_params(s, prm);
     if (rc) return rc;
-    if (p->batch < 1) return fail(BUNMPC_ERR_ARG, "solve: batch < 1");
+    // the time-slicing scratch (queue, parked states) is sized by max_batch
+    if (p->batch < 1 || p->batch > s->max_batch) return fail(BUNMPC_ERR_ARG, "solve: batch outside [1, max_batch]");
     if (!p->m.ptr || !p->rho.ptr || !p->x_init.ptr || !p->cnt_plan.ptr || !p->dt.ptr || !p->Qx.ptr || !p->qx.ptr ||
         !p->Qf.ptr || !p->qf.ptr || !p->lbx.ptr || !p->ubx.ptr || !p->L0.ptr)
         return fail(BUNMPC_ERR_ARG, "solve: null input field");
     CK(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;   // NULL is CUDA's default stream
     SolveArgs a;
-    a.B = p->batch; a.n = s->n; a.e = s->e; a.nx = s->nx; a.nf = s->nf;
+    a.B = p->batch; a.n = s->n;
     a.m = mk(p->m); a.rho = mk(p->rho); a.x_init = mk(p->x_init); a.cnt_plan = mk(p->cnt_plan); a.dt = mk(p->dt);
     a.Qx = mk(p->Qx); a.qx = mk(p->qx); a.Qf = mk(p->Qf); a.qf = mk(p->qf); a.lbx = mk(p->lbx); a.ubx = mk(p->ubx);
     a.L0 = mk(p->L0); a.X0 = mk(p->X0); a.F0 = mk(p->F0); a.P0 = mk(p->P0);
     a.X = out->X; a.F = out->F; a.P = out->P; a.L = out->L; a.viol = out->viol; a.viol_hist = out->viol_hist;
-    a.iters = out->iters; a.status = out->status; a.cycles = out->cycles; a.prof = nullptr;
-#ifdef BUNMPC_PHASE_PROF
-    a.prof = reinterpret_cast<long long *>(out->viol_hist);   // profiling build: the viol_hist buffer carries [B][64] counters
-    a.viol_hist = nullptr;
-#endif
+    a.iters = out->iters; a.status = out->status; a.cycles = out->cycles;
     a.max_outer = prm->max_outer; a.max_inner = prm->max_inner;
     a.tol = prm->tol; a.exit_tol = prm->exit_tol; a.beta = prm->beta; a.mu = prm->mu;
-    a.coef = s->coef; a.TF = s->TF.d; a.TX = s->TX.d; a.work_counter = s->work_counter; a.nav = s->nav;
-    const int smem = (int)(smem_doubles(s->n, s->e, prm->max_inner, s->nav) * sizeof(double));
-    if (smem > 200 * 1024) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: shared memory need exceeds 200 KB");
-    solve_fn fn = pick(s->e, prm->arith, s->n, s->nthreads, s->comb);
+    a.coef = s->coef; a.work_counter = s->work_counter;
+    const int smem = (int)smem_bytes_for(s->n, s->e, prm->max_inner, s->nthreads);
+    if (smem > kMaxSmemBytes) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: shared memory need exceeds one SM");
+    solve_fn fn = solve_pick(s->nthreads, prm->arith);
     int per_sm = s->ctas_per_sm[prm->arith];
     if (smem != s->smem_bytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->nthreads, smem));
     if (per_sm < 1) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: kernel does not fit on an SM");
@@ -416,8 +373,15 @@ static int dev_solution(bunmpc_solver *s, int B, const bunmpc_solution *want, in
     dev->viol_hist = nullptr;
     *hist_alloc = nullptr;
     if (want->viol_hist) {
-        CK(cudaMalloc(hist_alloc, Bs * (size_t)max_outer * sizeof(double)));
-        dev->viol_hist = *hist_alloc;
+        // staging for return_dyn_viol_hist: sized [max_batch][max_outer] the first time a history is asked for (and
+        // again only if a later call raises max_outer); solves that do not collect statistics never allocate
+        if (s->hist_cols < max_outer) {
+            CK(cudaStreamSynchronize(s->stream));
+            cudaFree(s->hist); s->hist = nullptr; s->hist_cols = 0;
+            CK(cudaMalloc(&s->hist, (size_t)s->max_batch * (size_t)max_outer * sizeof(double)));
+            s->hist_cols = max_outer;
+        }
+        dev->viol_hist = s->hist;
     }
     return BUNMPC_OK;
 }
@@ -446,7 +410,7 @@ int bunmpc_solve_compact_host(bunmpc_solver *s, const bunmpc_compact_problem *p,
     if (rc) return rc;
     rc = bunmpc_solve_compact_device(s, &d, prm, &dev, s->stream);
     if (!rc) rc = copy_out(s, p->batch, dev, out, prm->max_outer);
-    if (hist) cudaFree(hist);
+    (void)hist;
     return rc;
 }
 
@@ -474,7 +438,7 @@ int bunmpc_solve_expanded_host(bunmpc_solver *s, const bunmpc_expanded_problem *
     if (rc) return rc;
     rc = bunmpc_solve_expanded_device(s, &d, prm, &dev, s->stream);
     if (!rc) rc = copy_out(s, p->batch, dev, out, prm->max_outer);
-    if (hist) cudaFree(hist);
+    (void)hist;
     return rc;
 }
 

@@ -1,5 +1,6 @@
-// Getters of the solve_kernel instantiations.  Each group lives in its own translation unit (solve_inst.cu compiled
-// with -DINST_GROUP / -DINST_ARITH) so that the groups build in parallel; capi.cu only sees function pointers.
+// Getters of the solve_kernel instantiations.  Each (threads per CTA, arithmetic) pair lives in its own translation
+// unit (solve_inst.cu compiled with -DINST_NT / -DINST_ARITH) so that they build in parallel; capi.cu only sees
+// function pointers.
 #pragma once
 #include "kernels.cuh"
 
@@ -7,18 +8,32 @@ namespace bunmpc {
 
 typedef void (*solve_fn)(const SolveArgs);
 
-// group 0: horizons fixed at compile time (n = 20, 24, 30; nullptr for any other n)
-// group 3: doubled horizons fixed at compile time (n = 40; 48 and 60 with combined roles)
-// group 1: split warp roles, horizon read at run time
-// group 2: combined warp roles (long horizons), horizon read at run time
-// suffix: 0 = BUNMPC_ARITH_STRICT, 1 = BUNMPC_ARITH_FMA
-solve_fn solve_inst_0_0(int n, int nthreads);
-solve_fn solve_inst_0_1(int n, int nthreads);
-solve_fn solve_inst_1_0(int n, int nthreads);
-solve_fn solve_inst_1_1(int n, int nthreads);
-solve_fn solve_inst_2_0(int n, int nthreads);
-solve_fn solve_inst_2_1(int n, int nthreads);
-solve_fn solve_inst_3_0(int n, int nthreads);
-solve_fn solve_inst_3_1(int n, int nthreads);
+// Threads per CTA -> CTAs per SM the register budget is set for (__launch_bounds__): a thread keeps three Hessian
+// rows in registers and wants ~168 of them, so an SM (64K registers) holds 384 solver threads: 4 CTAs of 96, 3 of 128, ...
+// From 512 threads on the budget shrinks (128 / 80 / 64 registers) and the Hessian rows spill to local memory.
+#define BUNMPC_NT_LIST(X) X(32, 12) X(64, 6) X(96, 4) X(128, 3) X(192, 2) X(256, 1) X(384, 1) X(512, 1) X(768, 1) X(1024, 1)
+
+// smallest CTA size that holds a horizon: e*n force threads and 3(n+1) state/row threads
+inline int solve_threads(int n, int e)
+{
+    const int need = (e * n > 3 * (n + 1)) ? e * n : 3 * (n + 1);
+#define BUNMPC_PICK_NT(NT, MINB) if (need <= NT) return NT;
+    BUNMPC_NT_LIST(BUNMPC_PICK_NT)
+#undef BUNMPC_PICK_NT
+    return 0;
+}
+
+// suffix: threads per CTA, then 0 = BUNMPC_ARITH_STRICT, 1 = BUNMPC_ARITH_FMA
+#define BUNMPC_DECL_INST(NT, MINB) solve_fn solve_inst_##NT##_0(); solve_fn solve_inst_##NT##_1();
+BUNMPC_NT_LIST(BUNMPC_DECL_INST)
+#undef BUNMPC_DECL_INST
+
+inline solve_fn solve_pick(int nthreads, int arith)
+{
+#define BUNMPC_PICK_FN(NT, MINB) if (nthreads == NT) return arith ? solve_inst_##NT##_1() : solve_inst_##NT##_0();
+    BUNMPC_NT_LIST(BUNMPC_PICK_FN)
+#undef BUNMPC_PICK_FN
+    return nullptr;
+}
 
 }  // namespace bunmpc

@@ -28,9 +28,17 @@
  *      ASCENDING k, of (rho*A_ki)*A_kj; ATA_ij = 2*(Q_ij + S_ij) on the diagonal, 2*S_ij elsewhere.
  *  (4) ATbPk = 2*rho*A^T*bPk + q ([P]:38):  ((2*rho)*A_ki)*bPk_k summed over ASCENDING k, then + q_i.
  *  (5) dense reductions (norm, squaredNorm, dot, row*vec; [F]:16-18, [P]:47-48, [B]:102-111):
- *      tree_sum() below -- leaves in index order, blocks of `blk` leaves (32; 30 = ten 3-vectors for
- *      vectors of contact forces) zero-padded to 32 and summed by a radix-2 tree with strides
- *      16,8,4,2,1; block sums are combined the same way in groups of 32.
+ *      grouped_sum() below.  The leaves are first summed in TRIPLES, (l0 + l1) + l2:
+ *        - a vector indexed by contact forces (length 3*e*n): triple s = leaves 3s, 3s+1, 3s+2 (one
+ *          3-D force vector);
+ *        - a vector indexed by states or by constraint rows (length 9*(n+1)): triple s = 3t+a holds
+ *          leaves 9t+a, 9t+3+a, 9t+6+a (component a of the CoM, of the velocity and of the angular
+ *          momentum of knot t; for rows: the three dynamics rows of knot t that belong to axis a);
+ *        - any other vector: every leaf is its own group.
+ *      The group sums, in index order, are then summed by tree_sum(): blocks of 32, zero-padded,
+ *      radix-2 tree with strides 16,8,4,2,1; block sums are combined the same way in groups of 32.
+ *      (One group is what one GPU thread owns, one block is one warp.)  params.reduction = 32 selects
+ *      the plain tree over the leaves instead -- a rounding VARIANT kept for the sensitivity test.
  *  (6) x.transpose()*Q*d with diagonal Q ([P]:47):  ((x_i*Q_ii)*d_i) summed by (5).
  *  (7) cwiseMin(ub).cwiseMax(lb) ([F]:10):  t = (ub < u) ? ub : u;  y = (t < lb) ? lb : t.
  *  (8) everything else is evaluated exactly as the C++ expression parses (left to right).
@@ -44,8 +52,10 @@
 #include <string.h>
 
 #define GRAV 9.81           /* literal in [C]:62,104 */
-#define F_BLOCK 30          /* leaves per block for vectors of 3-D contact forces */
 #define X_BLOCK 32
+#define KIND_PLAIN 0        /* reduction layouts of rule (5) */
+#define KIND_FORCE 1
+#define KIND_STATE 2
 
 #define ALWAYS_INLINE static inline __attribute__((always_inline))
 #define MAD(FM, acc, a, b) ((FM) ? fma((a), (b), (acc)) : ((acc) + (a) * (b)))
@@ -59,7 +69,8 @@ void bicon_default_params(bicon_params *p)
     p->beta = 1.5;       /* [FH]:54 */
     p->mu = 1.0;         /* [FH]:60 */
     p->use_fma = 0;
-    p->f_block = F_BLOCK;
+    p->reduction = 0;
+    p->storage = 0;
 }
 
 /* ------------------------------------------------------------------ sparse patterns --------- */
@@ -333,6 +344,24 @@ static double tree_sum(const double *v, int n, int blk)
     return part[0];
 }
 
+/* rule (5): triples first, then the tree over the group sums */
+static double grouped_sum(const double *v, int len, int kind)
+{
+    double grp[4096];
+    if (kind == KIND_FORCE) {
+        int ns = len / 3;
+        for (int s = 0; s < ns; ++s) grp[s] = (v[3 * s] + v[3 * s + 1]) + v[3 * s + 2];
+        return tree_sum(grp, ns, 32);
+    }
+    if (kind == KIND_STATE) {
+        int nk = len / 9;
+        for (int t = 0; t < nk; ++t)
+            for (int a = 0; a < 3; ++a) grp[3 * t + a] = (v[9 * t + a] + v[9 * t + 3 + a]) + v[9 * t + 6 + a];
+        return tree_sum(grp, 3 * nk, 32);
+    }
+    return tree_sum(v, len, 32);
+}
+
 /* rule (1): row i of a CSR matrix times y */
 ALWAYS_INLINE double row_dot(const int FM, const int *rp, const int *cj, const double *val, int i, const double *y)
 {
@@ -345,11 +374,12 @@ ALWAYS_INLINE double row_dot(const int FM, const int *rp, const int *cj, const d
 
 /* ------------------------------------------------------------------ problem data ------------ */
 
-static int g_f32_storage = 0;   /* study only (BICON_F32_STORAGE=1): ATA_ and A_ entries rounded to binary32 */
-void bicon_set_f32_storage(int on) { g_f32_storage = on; }
+/* params.storage = 1 (the GPU's BUNMPC_ARITH_MIXED mode): the entries of ATA_ and of A_ are kept in binary32
+ * (round to nearest even) once set_data has formed them in binary64; every operation stays binary64. */
+ALWAYS_INLINE double store_round(int storage, double v) { return storage ? (double)(float)v : v; }
 
 /* ProblemData::set_data, [P]:31-39.  Q diagonal. */
-ALWAYS_INLINE void set_data(const int FM, const pattern *A, const double *Aval, double *Acsr,
+ALWAYS_INLINE void set_data(const int FM, const int storage, const pattern *A, const double *Aval, double *Acsr,
                             const gram *G, double *H, double *h, double *w,
                             const double *b, const double *P, const double *Q, const double *q, double rho)
 {
@@ -379,14 +409,14 @@ ALWAYS_INLINE void set_data(const int FM, const pattern *A, const double *Aval, 
         }
         h[i] = acc + q[i];
     }
-    if (g_f32_storage) {
-        for (int p = 0; p < G->nnz; ++p) H[p] = (double)(float)H[p];
-        for (int p = 0; p < A->nnz; ++p) Acsr[p] = (double)(float)Acsr[p];
+    if (storage) {
+        for (int p = 0; p < G->nnz; ++p) H[p] = store_round(storage, H[p]);
+        for (int p = 0; p < A->nnz; ++p) Acsr[p] = store_round(storage, Acsr[p]);
     }
 }
 
 typedef struct {
-    int nv, nr, blk, cone;
+    int nv, nr, vkind, rkind, cone;   /* reduction layouts of the variable- and row-indexed sums, rule (5) */
     const int *hrp, *hcj; const double *H, *h;
     const int *arp, *acj; const double *A, *w;
     const double *Q, *q, *lb, *ub;
@@ -436,16 +466,16 @@ ALWAYS_INLINE void fista(const int FM, bicon_ws *ws, const fista_data *D, double
                 ws->e2[i] = D->q[i] * (y1[i] - y[i]);
                 ws->e5[i] = g[i] * d[i];
             }
-            G_k_norm = sqrt(tree_sum(ws->e0, nv, D->blk));           /* [F]:16 */
+            G_k_norm = sqrt(grouped_sum(ws->e0, nv, D->vkind));           /* [F]:16 */
             for (int k = 0; k < nr; ++k) {                           /* [P]:48 */
                 double r1 = row_dot(FM, D->arp, D->acj, D->A, k, y1) + D->w[k];
                 double r0 = row_dot(FM, D->arp, D->acj, D->A, k, y) + D->w[k];
                 ws->e3[k] = r1 * r1; ws->e4[k] = r0 * r0;
             }
-            double t1 = tree_sum(ws->e1, nv, D->blk), t2 = tree_sum(ws->e2, nv, D->blk);
-            double n1 = tree_sum(ws->e3, nr, X_BLOCK), n0 = tree_sum(ws->e4, nr, X_BLOCK);
+            double t1 = grouped_sum(ws->e1, nv, D->vkind), t2 = grouped_sum(ws->e2, nv, D->vkind);
+            double n1 = grouped_sum(ws->e3, nr, D->rkind), n0 = grouped_sum(ws->e4, nr, D->rkind);
             double obj = t1 + t2 + (D->rho) * (n1 - n0);             /* [P]:47-48 */
-            double gd = tree_sum(ws->e5, nv, D->blk);
+            double gd = grouped_sum(ws->e5, nv, D->vkind);
             if (obj > gd + ((*L) / 2) * (G_k_norm * G_k_norm)) {     /* [F]:17-19 */
                 *L = D->beta * (*L);
                 ++*n_ls;
@@ -560,22 +590,24 @@ ALWAYS_INLINE int solve_impl(const int FM, bicon_ws *ws, const bicon_problem *p,
     int it_f = 0, it_x = 0, ls_f = 0, ls_x = 0, outer = 0, status = 1;
     double vnorm = 0.0;
 
-    fista_data Df = { nf, nx, (prm->f_block == 32 ? 32 : F_BLOCK), 1, ws->Gf.rp, ws->Gf.cj, ws->Hf, ws->hf,
+    const int plain = prm->reduction == 32;
+    const int kf = plain ? KIND_PLAIN : KIND_FORCE, kx = plain ? KIND_PLAIN : KIND_STATE;
+    fista_data Df = { nf, nx, kf, kx, 1, ws->Gf.rp, ws->Gf.cj, ws->Hf, ws->hf,
                       ws->Ax.rp, ws->Ax.cj, ws->Ax_csr, ws->w, p->Qf, p->qf, NULL, NULL,
                       p->rho, prm->mu, prm->beta };
-    fista_data Dx = { nx, nx, X_BLOCK, 0, ws->Gx.rp, ws->Gx.cj, ws->Hx, ws->hx,
+    fista_data Dx = { nx, nx, kx, kx, 0, ws->Gx.rp, ws->Gx.cj, ws->Hx, ws->hx,
                       ws->Af.rp, ws->Af.cj, ws->Af_csr, ws->w, p->Qx, p->qx, p->lbx, p->ubx,
                       p->rho, prm->mu, prm->beta };
 
     for (int i = 0; i < prm->max_outer; ++i) {
         /* optimizing for F, [B]:89-91 */
         compute_x_mat(ws, p, ws->X);
-        set_data(FM, &ws->Ax, ws->Ax_val, ws->Ax_csr, &ws->Gf, ws->Hf, ws->hf, ws->w,
+        set_data(FM, prm->storage, &ws->Ax, ws->Ax_val, ws->Ax_csr, &ws->Gf, ws->Hf, ws->hf, ws->w,
                  ws->b_x, ws->P, p->Qf, p->qf, p->rho);
         fista(FM, ws, &Df, ws->F, &L_f, prm->max_inner, prm->tol, &it_f, &ls_f);
         /* optimizing for X, [B]:94-96 */
         compute_f_mat(ws, p, ws->F);
-        set_data(FM, &ws->Af, ws->Af_val, ws->Af_csr, &ws->Gx, ws->Hx, ws->hx, ws->w,
+        set_data(FM, prm->storage, &ws->Af, ws->Af_val, ws->Af_csr, &ws->Gx, ws->Hx, ws->hx, ws->w,
                  ws->b_f, ws->P, p->Qx, p->qx, p->rho);
         fista(FM, ws, &Dx, ws->X, &L_x, prm->max_inner, prm->tol, &it_x, &ls_x);
         /* dyn_violation = A_f * x_k - b_f;  P_k_ += dyn_violation, [B]:98-99 */
@@ -584,7 +616,7 @@ ALWAYS_INLINE int solve_impl(const int FM, bicon_ws *ws, const bicon_problem *p,
             ws->P[k] += ws->viol[k];
             ws->e0[k] = ws->viol[k] * ws->viol[k];
         }
-        vnorm = sqrt(tree_sum(ws->e0, nx, X_BLOCK));
+        vnorm = sqrt(grouped_sum(ws->e0, nx, kx));
         ++outer;
         if (out->viol_hist) out->viol_hist[i] = vnorm;               /* [B]:102-104 */
         if (isnan(vnorm)) { status = 2; break; }                      /* [B]:106-109 */

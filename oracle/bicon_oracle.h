@@ -41,9 +41,11 @@ typedef struct {
     int    use_fma;     /* 0: separate multiply and add everywhere (x86-64 Release build of the
                            reference has no FMA); 1: the fused variant mirrored by the GPU's
                            BUNMPC_ARITH_FMA mode */
-    int    f_block;     /* leaves per reduction block for vectors of contact forces: 30 (ten 3-vectors, the
-                           order the GPU kernels use; default) or 32 (the order of oracle/refshim, used only
-                           to cross-check this restatement against the reference's own sources) */
+    int    reduction;   /* 0: the canonical order of dense sums (triples, then a tree over 32-blocks of the
+                           triple sums -- rule (5) in bicon_oracle.c; what oracle/refshim and the GPU kernels
+                           use); 32: a plain tree over 32-leaf blocks, a rounding variant for sensitivity tests */
+    int    storage;     /* 0: ATA_ and A_ entries in binary64; 1: rounded to binary32 after set_data (arithmetic
+                           stays binary64) -- the GPU's BUNMPC_ARITH_MIXED mode */
 } bicon_params;
 
 void bicon_default_params(bicon_params *p);
@@ -89,10 +91,6 @@ void      bicon_ws_destroy(bicon_ws *ws);
 
 /* BiConvexMP::optimize (biconvex.cpp:80-120). Returns 0, or -1 on bad arguments. */
 int bicon_solve(bicon_ws *ws, const bicon_problem *p, const bicon_params *prm, bicon_result *out);
-
-/* Study hook (not part of the restatement): round the entries of ATA_ and A_ to binary32 after set_data, all
- * arithmetic stays binary64 -- used to size a mixed-precision mode (DESIGN.md, FP32 note). */
-void bicon_set_f32_storage(int on);
 
 /* Host-side builders (biconvex.cpp:27-78). */
 void bicon_create_bound_constraints(int n_col, int n_eff, const double *cnt_plan,

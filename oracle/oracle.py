@@ -20,7 +20,7 @@ _lib = None
 class Params(C.Structure):
     _fields_ = [("max_outer", C.c_int), ("max_inner", C.c_int), ("tol", C.c_double),
                 ("exit_tol", C.c_double), ("beta", C.c_double), ("mu", C.c_double),
-                ("use_fma", C.c_int), ("f_block", C.c_int)]
+                ("use_fma", C.c_int), ("reduction", C.c_int), ("storage", C.c_int)]
 
 
 def build(force: bool = False) -> str:

@@ -34,6 +34,8 @@ int ref_solve(void *h, int n_col, int n_eff, double rho, const double *x_init, c
 {
     BiConvexMP &mp = *static_cast<BiConvexMP *>(h);
     const int n = n_col, e = n_eff, nx = 9 * (n + 1), nf = 3 * e * n;
+    Eigen::shim::layout().n = n;                      // lets the stand-in pick the reduction layout by vector length
+    Eigen::shim::layout().e = e;
     mp.set_rho(rho);
     for (int i = 0; i < n; ++i) {                      // abstract_cyclic_gen.py:391
         Eigen::MatrixXd cp(e, 4);

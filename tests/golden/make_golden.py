@@ -3,12 +3,14 @@
 Run in the build container (where /root/reference is mounted and oracle/_ref has been built by
 `make -C oracle/refshim`):   python tests/golden/make_golden.py
 
-For every case the file stores the compact inputs of the solve and four result sets:
+For every case the file stores the compact inputs of the solve and five result sets:
   ref    : the reference's OWN sources (biconvex.cpp, centroidal.cpp, problem.cpp, fista.cpp compiled in place
            against oracle/refshim's Eigen stand-in), driven through its own setters and optimize()
-  o32    : the oracle with 32-leaf reduction blocks everywhere   (must equal `ref` bit for bit)
-  o30    : the oracle in its default order (30-leaf blocks for force vectors) = what the GPU STRICT mode reproduces
-  o30f   : same with fused multiply-adds = what the GPU FMA mode reproduces
+  oc     : the oracle in the canonical evaluation order (must equal `ref` bit for bit) = what the GPU STRICT mode
+           reproduces
+  ocf    : same with fused multiply-adds = what the GPU FMA mode reproduces
+  ocm    : same with ATA_ / A_ entries stored in binary32 = what the GPU MIXED mode reproduces
+  o32    : the oracle with plain 32-leaf reduction blocks -- a rounding variant (tests/test_oracle_golden.py)
 """
 import os
 import sys
@@ -51,13 +53,14 @@ def main():
             v = getattr(b, f)
             if v is not None:
                 out[f"{name}/in/{f}"] = v
-        sets = {"o32": oracle.solve(b, params=oracle.default_params(f_block=32)),
-                "o30": oracle.solve(b),
-                "o30f": oracle.solve(b, params=oracle.default_params(use_fma=1))}
+        sets = {"o32": oracle.solve(b, params=oracle.default_params(reduction=32)),
+                "oc": oracle.solve(b),
+                "ocf": oracle.solve(b, params=oracle.default_params(use_fma=1)),
+                "ocm": oracle.solve(b, params=oracle.default_params(storage=1))}
         if oracle.ref_available():
             sets["ref"] = oracle.ref_solve(b)
-            same = all(np.array_equal(sets["ref"][k], sets["o32"][k], equal_nan=True) for k in RES if k != "status")
-            print(f"{name:24s} ref == o32: {same}   iters {sets['ref']['iters'].tolist()}")
+            same = all(np.array_equal(sets["ref"][k], sets["oc"][k], equal_nan=True) for k in RES if k != "status")
+            print(f"{name:24s} ref == oc: {same}   iters {sets['ref']['iters'].tolist()}")
             assert same, name
         for sname, res in sets.items():
             for k in RES:
@@ -77,7 +80,7 @@ def load(path=None):
         kw = {f: z[f"{name}/in/{f}"] for f in FIELDS if f"{name}/in/{f}" in z.files}
         b = CentroidalBatch(int(z[f"{name}/n_col"]), int(z[f"{name}/n_eff"]), **kw)
         sets = {}
-        for sname in ("ref", "o32", "o30", "o30f"):
+        for sname in ("ref", "oc", "ocf", "ocm", "o32"):
             if f"{name}/{sname}/X" in z.files:
                 sets[sname] = {k: z[f"{name}/{sname}/{k}"] for k in RES}
         res.append((str(name), b, sets))

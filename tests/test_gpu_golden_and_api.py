@@ -22,8 +22,8 @@ def test_gpu_reproduces_golden(name, batch, sets):
     sol = s.solve(batch)
     solf = s.solve(batch, arith=ARITH_FMA)
     for k in RES:
-        assert same(getattr(sol, k), sets["o30"][k]), f"{name}/o30/{k}"
-        assert same(getattr(solf, k), sets["o30f"][k]), f"{name}/o30f/{k}"
+        assert same(getattr(sol, k), sets["oc"][k]), f"{name}/oc/{k}"
+        assert same(getattr(solf, k), sets["ocf"][k]), f"{name}/ocf/{k}"
         if k != "status":
             assert same(getattr(sol, k), sets["ref"][k]), f"{name}/ref/{k}"
 
