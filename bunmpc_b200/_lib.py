@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbunmpc.so")
+# BUNMPC_LIB selects another build of the same library (profiling / experiment builds); never a fallback
+LIB_PATH = os.environ.get("BUNMPC_LIB") or os.path.join(_HERE, "csrc", "libbunmpc.so")
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 CONVERGED, MAX_ITERS, NAN = 0, 1, 2

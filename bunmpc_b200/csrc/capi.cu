@@ -245,11 +245,21 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     a.max_outer = prm->max_outer; a.max_inner = prm->max_inner;
     a.tol = prm->tol; a.exit_tol = prm->exit_tol; a.beta = prm->beta; a.mu = prm->mu;
     a.coef = s->coef; a.work_counter = s->work_counter;
+    a.S = make_layout(s->n, s->e, prm->max_inner, s->nthreads / 32);
     const int smem = (int)smem_bytes_for(s->n, s->e, prm->max_inner, s->nthreads);
     if (smem > kMaxSmemBytes) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: shared memory need exceeds one SM");
     solve_fn fn = solve_pick(s->nthreads, prm->arith);
     int per_sm = s->ctas_per_sm[prm->arith];
-    if (smem != s->smem_bytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->nthreads, smem));
+    if (const char *ev = getenv("BUNMPC_CTAS")) {      // experiment: occupancy variants of the 96-thread STRICT kernel
+        solve_fn alt = (s->nthreads == 96 && prm->arith == 0) ? solve_inst_x96(0, atoi(ev)) : nullptr;
+        if (alt) {
+            fn = alt;
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->nthreads, smem));
+        }
+    }
+    else if (smem != s->smem_bytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->nthreads, smem));
     if (per_sm < 1) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: kernel does not fit on an SM");
     long long grid = (long long)s->num_sms * per_sm;
     if (grid > a.B) grid = a.B;

@@ -12,6 +12,8 @@ typedef void (*solve_fn)(const SolveArgs);
 // rows in registers and wants ~168 of them, so an SM (64K registers) holds 384 solver threads: 4 CTAs of 96, 3 of 128, ...
 // From 512 threads on the budget shrinks (128 / 80 / 64 registers) and the Hessian rows spill to local memory.
 #define BUNMPC_NT_LIST(X) X(32, 12) X(64, 6) X(96, 4) X(128, 3) X(192, 2) X(256, 1) X(384, 1) X(512, 1) X(768, 1) X(1024, 1)
+// experimental occupancy variants of the 96-thread kernel (BUNMPC_CTAS=5|6 in the environment, see capi.cu)
+solve_fn solve_inst_x96(int arith, int ctas);
 
 // smallest CTA size that holds a horizon: e*n force threads and 3(n+1) state/row threads
 inline int solve_threads(int n, int e)

@@ -116,14 +116,15 @@ def test_time_sliced_instances(oracle):
     _require_gpu()
     from bunmpc_b200 import synthetic
     from bunmpc_b200.solver import BatchSolver
-    b = synthetic.perturbed(333, "solo12", "trot", seed=5)
-    s = BatchSolver(b.n_col, b.n_eff, max_batch=333)
-    assert 333 > s.kernel_info()["num_sms"] * s.kernel_info()["ctas_per_sm"]
+    probe = BatchSolver(20, 4, max_batch=1)
+    B = probe.kernel_info()["num_sms"] * probe.kernel_info()["ctas_per_sm"] + 141      # more than fit at once
+    b = synthetic.perturbed(B, "solo12", "trot", seed=5)
+    s = BatchSolver(b.n_col, b.n_eff, max_batch=B)
     sol = s.solve(b, viol_hist=True)
     ref = oracle.solve(b, n_threads=16)
     assert_same(sol, ref, "time-sliced")
     assert sol.iters[:, 0].max() > 16                       # some instances were parked at least twice
-    for i in (0, 100, 332):                                 # history: one entry per outer iteration, NaN after the exit
+    for i in (0, 100, B - 1):                               # history: one entry per outer iteration, NaN after the exit
         k = sol.iters[i, 0]
         assert np.isfinite(sol.viol_hist[i, :k]).all() and np.isnan(sol.viol_hist[i, k:]).all()
         assert sol.viol_hist[i, k - 1] == sol.viol[i]
