@@ -241,7 +241,11 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     a.Qx = mk(p->Qx); a.qx = mk(p->qx); a.Qf = mk(p->Qf); a.qf = mk(p->qf); a.lbx = mk(p->lbx); a.ubx = mk(p->ubx);
     a.L0 = mk(p->L0); a.X0 = mk(p->X0); a.F0 = mk(p->F0); a.P0 = mk(p->P0);
     a.X = out->X; a.F = out->F; a.P = out->P; a.L = out->L; a.viol = out->viol; a.viol_hist = out->viol_hist;
-    a.iters = out->iters; a.status = out->status; a.cycles = out->cycles;
+    a.iters = out->iters; a.status = out->status; a.cycles = out->cycles; a.prof = nullptr;
+#ifdef BUNMPC_PHASE_PROF
+    a.prof = reinterpret_cast<long long *>(out->viol_hist);   // profiling build: the viol_hist buffer carries [B][16] counters
+    a.viol_hist = nullptr;
+#endif
     a.max_outer = prm->max_outer; a.max_inner = prm->max_inner;
     a.tol = prm->tol; a.exit_tol = prm->exit_tol; a.beta = prm->beta; a.mu = prm->mu;
     a.coef = s->coef; a.work_counter = s->work_counter;

@@ -1,23 +1,26 @@
-"""Per-phase cycle totals of the FISTA fast path (profiling build profiles/libbunmpc_prof.so built with
--DBUNMPC_PHASE_PROF; clock reads are ordered after the data they follow by a resolved branch).
-Per instance and problem (F, X) the kernel accumulates, for lane 0 of variable warp 0, row warp 0 and the scalar
-warp, the cycles spent in: 0 set-up, 1 gradient, 2 division+projection, 3 variable sums, 4 momentum+stores,
-5 barrier wait, 6 row work, 7 scalar work, 8 tail.  GPU box only."""
-import sys, os, numpy as np
+"""Per-phase cycle totals of one FISTA iteration (profiling build profiles/libbunmpc_prof.so, built by
+`make -C bunmpc_b200/csrc prof` with -DBUNMPC_PHASE_PROF).  Per instance and problem (F, X) the kernel accumulates,
+for thread 0, the cycles between: 0 start of the iteration -> end of the first phase (gradient, prox, sums, row sums of
+y_k), 1 first barrier, 2 second phase (row sums of y_k_1, momentum store, warp reduction), 3 second barrier,
+4 totals + line-search test.  GPU box only:   python profiles/phase_probe.py [B]"""
+import os
+import sys
+
+import numpy as np
+
 sys.path.insert(0, '.')
-from bunmpc_b200 import _lib
-_lib.LIB_PATH = os.path.join('profiles', 'libbunmpc_prof.so')
+os.environ["BUNMPC_LIB"] = os.path.join('profiles', 'libbunmpc_prof.so')
 from bunmpc_b200 import synthetic
 from bunmpc_b200.solver import BatchSolver
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 b = synthetic.config(1, B=B, seed=0)
-s = BatchSolver(b.n_col, b.n_eff, max_batch=1024)
-sol = s.solve(b, viol_hist=True)       # profiling build: the viol_hist buffer of each instance carries 64 counters
-tr = sol.viol_hist.view(np.int64).reshape(-1)[: B * 64].reshape(B, 64).astype(np.float64)
-names = ["setup", "grad", "proj", "sums", "mom+sts", "barrier", "row", "scalar", "tail"]
+s = BatchSolver(b.n_col, b.n_eff, max_batch=B)
+sol = s.solve(b, viol_hist=True)       # profiling build: the viol_hist buffer of each instance carries 16 counters
+tr = sol.viol_hist.view(np.int64).reshape(-1)[: B * 16].reshape(B, 16).astype(np.float64)
+names = ["phase 1", "barrier 1", "phase 2", "barrier 2", "decision"]
 for prob, pn, itc in ((0, "F", sol.iters[:, 1]), (1, "X", sol.iters[:, 2])):
-    for role, rn in enumerate(("variable warp 0", "row warp 0", "scalar warp")):
-        c = tr[:, 32 * prob + 9 * role: 32 * prob + 9 * role + 9]
-        per = c.sum(0) / itc.sum()
-        print(f"{pn} {rn:16s} cycles per inner iteration: " + "  ".join(f"{n} {v:6.0f}" for n, v in zip(names, per)) + f"   total {per.sum():6.0f}")
+    per = tr[:, 8 * prob: 8 * prob + 5].sum(0) / itc.sum()
+    print(f"B={B} {pn} cycles per inner iteration (thread 0): " + "  ".join(f"{n} {v:6.0f}" for n, v in zip(names, per))
+          + f"   total {per.sum():6.0f}")
+print("kernel", s.kernel_info(), "cycles per inner iteration per CTA", sol.cycles.sum() / (sol.iters[:, 1] + sol.iters[:, 2]).sum())
