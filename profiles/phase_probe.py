@@ -16,11 +16,11 @@ from bunmpc_b200.solver import BatchSolver
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 b = synthetic.config(1, B=B, seed=0)
 s = BatchSolver(b.n_col, b.n_eff, max_batch=B)
-sol = s.solve(b, viol_hist=True)       # profiling build: the viol_hist buffer of each instance carries 16 counters
-tr = sol.viol_hist.view(np.int64).reshape(-1)[: B * 16].reshape(B, 16).astype(np.float64)
-names = ["phase 1", "barrier 1", "phase 2", "barrier 2", "decision"]
+sol = s.solve(b, viol_hist=True)       # profiling build: the viol_hist buffer of each instance carries 32 counters
+tr = sol.viol_hist.view(np.int64).reshape(-1)[: B * 32].reshape(B, 32).astype(np.float64)
+names = ["rest of phase 1 (F: row sums of y_k)", "barrier 1", "phase 2", "barrier 2", "decision", "loads+gradient", "division", "projection", "sums+momentum"]
 for prob, pn, itc in ((0, "F", sol.iters[:, 1]), (1, "X", sol.iters[:, 2])):
-    per = tr[:, 8 * prob: 8 * prob + 5].sum(0) / itc.sum()
+    per = tr[:, 16 * prob: 16 * prob + 9].sum(0) / itc.sum()
     print(f"B={B} {pn} cycles per inner iteration (thread 0): " + "  ".join(f"{n} {v:6.0f}" for n, v in zip(names, per))
           + f"   total {per.sum():6.0f}")
 print("kernel", s.kernel_info(), "cycles per inner iteration per CTA", sol.cycles.sum() / (sol.iters[:, 1] + sol.iters[:, 2]).sum())
