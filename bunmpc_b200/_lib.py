@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("BUNMPC_LIB") or os.path.join(_HERE, "csrc", "libbunmp
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 CONVERGED, MAX_ITERS, NAN = 0, 1, 2
-ARITH_STRICT, ARITH_FMA = 0, 1
+ARITH_STRICT, ARITH_FMA, ARITH_MIXED = 0, 1, 2
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)

@@ -46,7 +46,7 @@ struct bunmpc_solver {
     int hist_cols = 0;
     long long launches = 0;
     int nthreads = 0, smem_bytes = 0;
-    int ctas_per_sm[2] = {0, 0};     // per arith
+    int ctas_per_sm[3] = {0, 0, 0};  // per arith
 };
 
 static size_t smem_bytes_for(int n, int e, int max_inner, int nthreads)
@@ -153,7 +153,7 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
 
     // opt in to the shared memory the kernel needs and record occupancy
     s->smem_bytes = (int)smem_bytes_for(n, e, 150, nthreads);
-    for (int arith = 0; arith < 2; ++arith) {
+    for (int arith = 0; arith < 3; ++arith) {
         solve_fn fn = solve_pick(nthreads, arith);
         CKS(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
         CKS(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -191,7 +191,7 @@ static int check_params(const bunmpc_solver *s, const bunmpc_params *prm)
     if (!prm) return fail(BUNMPC_ERR_ARG, "null params");
     if (prm->max_outer < 0 || prm->max_inner < 1 || prm->max_inner > s->coef_len)
         return fail(BUNMPC_ERR_ARG, "max_inner/max_outer out of range");
-    if (prm->arith != BUNMPC_ARITH_STRICT && prm->arith != BUNMPC_ARITH_FMA)
+    if (prm->arith != BUNMPC_ARITH_STRICT && prm->arith != BUNMPC_ARITH_FMA && prm->arith != BUNMPC_ARITH_MIXED)
         return fail(BUNMPC_ERR_UNSUPPORTED, "unknown arith mode");
     // a rejected step multiplies L by beta until it is accepted (fista.cpp:19): beta <= 1 would spin forever inside a
     // persistent kernel; the tolerances only have to be comparable
@@ -254,8 +254,8 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     if (smem > kMaxSmemBytes) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: shared memory need exceeds one SM");
     solve_fn fn = solve_pick(s->nthreads, prm->arith);
     int per_sm = s->ctas_per_sm[prm->arith];
-    if (const char *ev = getenv("BUNMPC_CTAS")) {      // experiment: occupancy variants of the 96-thread STRICT kernel
-        solve_fn alt = (s->nthreads == 96 && prm->arith == 0) ? solve_inst_x96(0, atoi(ev)) : nullptr;
+    if (const char *ev = getenv("BUNMPC_CTAS")) {      // experiment: occupancy variants of the 96-thread MIXED kernel
+        solve_fn alt = (s->nthreads == 96 && prm->arith == 2) ? solve_inst_x96(2, atoi(ev)) : nullptr;
         if (alt) {
             fn = alt;
             CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));

@@ -16,12 +16,12 @@ constexpr int kMinBlocks = BUNMPC_NT_LIST(BUNMPC_MINB_OF) 1;
 
 solve_fn INST_NAME() { return solve_kernel<4, INST_ARITH, INST_NT, kMinBlocks>; }
 
-#if INST_NT == 96 && INST_ARITH == 0
+#if INST_NT == 96 && INST_ARITH == 2
 solve_fn solve_inst_x96(int arith, int ctas)
 {
     (void)arith;
-    if (ctas == 5) return solve_kernel<4, 0, 96, 5>;
-    if (ctas == 6) return solve_kernel<4, 0, 96, 6>;
+    if (ctas == 5) return solve_kernel<4, 2, 96, 5>;
+    if (ctas == 6) return solve_kernel<4, 2, 96, 6>;
     return nullptr;
 }
 #endif

@@ -25,14 +25,14 @@ inline int solve_threads(int n, int e)
     return 0;
 }
 
-// suffix: threads per CTA, then 0 = BUNMPC_ARITH_STRICT, 1 = BUNMPC_ARITH_FMA
-#define BUNMPC_DECL_INST(NT, MINB) solve_fn solve_inst_##NT##_0(); solve_fn solve_inst_##NT##_1();
+// suffix: threads per CTA, then 0 = BUNMPC_ARITH_STRICT, 1 = BUNMPC_ARITH_FMA, 2 = BUNMPC_ARITH_MIXED
+#define BUNMPC_DECL_INST(NT, MINB) solve_fn solve_inst_##NT##_0(); solve_fn solve_inst_##NT##_1(); solve_fn solve_inst_##NT##_2();
 BUNMPC_NT_LIST(BUNMPC_DECL_INST)
 #undef BUNMPC_DECL_INST
 
 inline solve_fn solve_pick(int nthreads, int arith)
 {
-#define BUNMPC_PICK_FN(NT, MINB) if (nthreads == NT) return arith ? solve_inst_##NT##_1() : solve_inst_##NT##_0();
+#define BUNMPC_PICK_FN(NT, MINB) if (nthreads == NT) return arith == 2 ? solve_inst_##NT##_2() : (arith ? solve_inst_##NT##_1() : solve_inst_##NT##_0());
     BUNMPC_NT_LIST(BUNMPC_PICK_FN)
 #undef BUNMPC_PICK_FN
     return nullptr;

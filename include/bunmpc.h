@@ -32,8 +32,11 @@ enum {
 enum { BUNMPC_CONVERGED = 0, BUNMPC_MAX_ITERS = 1, BUNMPC_NAN = 2 };
 
 /* arithmetic variants; BUNMPC_ARITH_STRICT reproduces the oracle's unfused operation order bit for bit,
- * BUNMPC_ARITH_FMA fuses the multiply-adds of the mat-vecs (oracle: use_fma = 1). */
-enum { BUNMPC_ARITH_STRICT = 0, BUNMPC_ARITH_FMA = 1 };
+ * BUNMPC_ARITH_FMA fuses the multiply-adds of the mat-vecs (oracle: use_fma = 1),
+ * BUNMPC_ARITH_MIXED keeps the entries of ATA_ = 2(Q + rho A^T A) and of A_ in binary32 once set_data has formed them
+ * (every operation, the line search and the exit tests stay binary64; oracle: storage = 1): the "FP32 mode" of the
+ * path, a tolerance mode (1e-3 relative on forces and CoM/momentum), bit-exact against its own oracle twin. */
+enum { BUNMPC_ARITH_STRICT = 0, BUNMPC_ARITH_FMA = 1, BUNMPC_ARITH_MIXED = 2 };
 
 typedef struct bunmpc_solver bunmpc_solver;   /* opaque: device, stream, tables, staging buffers */
 
