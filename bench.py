@@ -4,7 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 A step = one pass of the hot path (create_* + BiConvexMP::optimize for every instance) over one batch of
-synthetic perturbed Solo12-trot states: BASELINE config[1], B = 1024 instances per GPU, horizon 20.
+synthetic perturbed Solo12-trot states: BASELINE config[1], 1024 instances per GPU, horizon 20.  With N GPUs the
+step is bunmpc_b200.dist.ShardedSolver.step on ONE global batch of 1024 N instances sharded interleaved (instance
+i -> rank i mod N): solve, then the path's two exchange steps over NCCL -- all_gather of the solved trajectories and
+all_reduce of the 17 posterior sufficient statistics.
   value : solves/s with the batch resident in HBM (CUDA events on the launching stream, L2 flushed
           between steps, max over ranks)
   e2e   : the same through the host-buffer C ABI call (pinned host inputs -> H2D -> kernels -> D2H)
@@ -123,47 +126,84 @@ def run_cpu(batch, cores, max_instances, budget_s=25.0):
     return n / dt, n, dt
 
 
-def smem_roofline(iters, k_time, clocks, info):
-    wf_per_iter = 572.0
-    mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
-    if not mhz or not k_time:
+def ncu_constants():
+    """Per-launch counters of the profiled solve kernel, written by profiles/summarize.py from an ncu report of THIS
+    workload (with the commit of the kernel they belong to); None when the file is missing."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_constants.json")))
+    except Exception:
         return None
+
+
+def smem_roofline(iters, k_time, clocks, info, ncu):
+    """Shared-memory data pipe: wavefronts per inner iteration from the ncu capture (l1tex__data_pipe_lsu_wavefronts_
+    mem_shared of the profiled launch / its inner iterations), scaled by the live iteration counters and kernel time."""
+    mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
+    if not ncu or not mhz or not k_time or not ncu.get("smem_wavefronts_per_inner_iteration"):
+        return None
+    wf_per_iter = float(ncu["smem_wavefronts_per_inner_iteration"])
     wf = wf_per_iter * float(iters[:, 1].sum() + iters[:, 2].sum())
     ach = wf / (k_time * mhz * 1e6 * info["num_sms"])
     return {"bound": "shared-memory data pipe", "achieved": ach, "peak": 1.0, "unit": "wavefronts/clk/SM", "frac": ach,
             "peak_source": "nominal 1 wavefront (128 B) per clock per SM",
-            "wavefronts_per_inner_iteration": wf_per_iter,
-            "ncu_pct_of_peak_sustained_elapsed": 57.8}   # l1tex__data_pipe_lsu_wavefronts_mem_shared, profiled launch
+            "wavefronts_per_inner_iteration": wf_per_iter, "source": ncu.get("source")}
 
 
-def other_workloads(device, arith):
-    """Short single-GPU runs of the other BASELINE.json configs (per-GPU shard sizes), host-buffer path, one warm-up
-    + one timed solve each: reported for context, not part of `value`."""
-    from bunmpc_b200 import synthetic
-    from bunmpc_b200.solver import BatchSolver
+def other_workloads(device, arith, world=1, rank=0):
+    """Short runs of the other BASELINE.json configs at their real sizes: total batch / world instances per GPU
+    (16 384 Go2 trot, 4 096 bound n=48 / jump n=60, 65 536 Bayes samples over 8 GPUs -> 2048 / 512 / 8192 per GPU; a
+    single-GPU run measures that per-GPU shard).  Device-resident ShardedSolver.step (solve + statistics + gathers under
+    world > 1), one warm-up + one timed step each, max over ranks: reported for context, not part of `value`."""
+    import torch
+    import torch.distributed as dist
+    from bunmpc_b200 import SolverParams, synthetic
+    from bunmpc_b200.dist import ShardedSolver
+    from bunmpc_b200.motions import GO2_RETUNE_SOLVER
     out = {}
-    cases = [("config2_go2_trot_B2048_n20 (16384/8 GPUs)", lambda: synthetic.config(2, B=2048)),
-             ("config3_go2_bound_B512_n48 (reference algorithm diverges: cone quirk Q2, see DESIGN.md 6)", lambda: synthetic.config(3, B=512)),
-             ("solo12_bound_B1024_n24 (bound gait, its own horizon)", lambda: synthetic.perturbed(1024, "solo12", "bound", seed=0)),
-             ("solo12_jump_B1024_n30 (jump gait, its own horizon)", lambda: synthetic.perturbed(1024, "solo12", "jump", seed=0)),
-             ("solo12_bound_B1024_n48 (config 3 gait and horizon, Solo12 mass)", lambda: synthetic.perturbed(1024, "solo12", "bound", seed=0, horizon_scale=2.0)),
-             ("solo12_jump_B512_n60", lambda: synthetic.perturbed(512, "solo12", "jump", seed=0, horizon_scale=2.0)),
-             ("config4_bayes_goal+weight_samples_B8192_n20 (65536/8 GPUs)", lambda: synthetic.config(4, B=8192)),
-             ("solo12_trot_B8192_n20 (saturated)", lambda: synthetic.config(1, B=8192, seed=1))]
-    for name, make in cases:
-        b = make()
-        s = BatchSolver(b.n_col, b.n_eff, max_batch=b.B, device=device)
-        s.solve(b.select(np.arange(min(b.B, 256))), arith=arith)
-        t0 = time.perf_counter()
-        sol = s.solve(b, arith=arith)
-        dt = time.perf_counter() - t0
-        out[name] = {"solves_per_s_e2e": b.B / dt, "ms": 1e3 * dt, "n_col": b.n_col,
-                     "outer_mean": float(sol.iters[:, 0].mean()), "inner_mean": float(sol.iters[:, 1:3].sum(1).mean()),
-                     "converged_frac": float((sol.status == 0).mean()), "nan_frac": float((sol.status == 2).mean())}
-        s.close()
+    seed = 100 + rank     # the global batch of a config = the union of the per-rank shards (i.i.d. instances)
+    retuned = SolverParams(**GO2_RETUNE_SOLVER)
+    cases = [("config2_go2_trot_16384 (Solo12 gait records, Go2 mass: the reference algorithm diverges, DESIGN.md)", 2048, lambda B: synthetic.config(2, B=B, seed=seed), None),
+             ("config2_go2_trot_16384_RETUNED (non-reference weights, mu, exit_tol: motions.GO2_RETUNE_*)", 2048, lambda B: synthetic.perturbed(B, "go2_retuned", "trot", seed=seed), retuned),
+             ("config3_go2_bound_n48_4096 (reference algorithm diverges)", 512, lambda B: synthetic.config(3, B=B, seed=seed), None),
+             ("config3_go2_bound_n48_4096_RETUNED (non-reference)", 512, lambda B: synthetic.perturbed(B, "go2_retuned", "bound", seed=seed, horizon_scale=2.0), retuned),
+             ("config3_solo12_bound_n48_4096 (config 3 gait and horizon, Solo12 mass)", 512, lambda B: synthetic.perturbed(B, "solo12", "bound", seed=seed, horizon_scale=2.0), None),
+             ("config3_solo12_jump_n60_4096", 512, lambda B: synthetic.perturbed(B, "solo12", "jump", seed=seed, horizon_scale=2.0), None),
+             ("solo12_bound_n24_8192 (bound gait, its own horizon)", 1024, lambda B: synthetic.perturbed(B, "solo12", "bound", seed=seed), None),
+             ("solo12_jump_n30_8192 (jump gait, its own horizon)", 1024, lambda B: synthetic.perturbed(B, "solo12", "jump", seed=seed), None),
+             ("config4_bayes_goal+weight_samples_65536", 8192, lambda B: synthetic.config(4, B=B, seed=seed), None),
+             ("solo12_trot_65536 (saturated)", 8192, lambda B: synthetic.config(1, B=B, seed=seed), None)]
+    for name, per_gpu, make, prm in cases:
+        b = make(per_gpu)
+        sh = ShardedSolver(b.n_col, b.n_eff, shard_batch=per_gpu, device=device)
+        sh.upload_shard(b)
+        sh.step(params=prm, arith=arith)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        o = sh.step(params=prm, arith=arith)
+        e1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
+        st = o["status"]
+        agg = torch.tensor([float((st == 0).sum()), float((st == 2).sum()), float(o["iters"][:, 0].sum()),
+                            float(o["iters"][:, 1:3].sum())], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        tot = world * per_gpu
+        agg = agg.cpu().numpy()
+        out[name] = {"solves_per_s": tot / float(tt.item()), "ms": 1e3 * float(tt.item()), "instances": tot,
+                     "per_gpu": per_gpu, "n_col": b.n_col, "outer_mean": agg[2] / tot, "inner_mean": agg[3] / tot,
+                     "converged_frac": agg[0] / tot, "nan_frac": agg[1] / tot,
+                     "posterior_stats_N": float(sh.stats[0].item())}
+        sh.solver.close()
+    if world > 1:
+        return out
     # f-1: only the centroidal states cross PCIe; contact plan and references are built on the device
     from bunmpc_b200.motions import GAITS, ROBOTS
-    import torch
+    from bunmpc_b200.solver import BatchSolver
     rb, gp = ROBOTS["solo12"], GAITS["solo12"]["trot"]
     rng = np.random.default_rng(0)
     B = 1024
@@ -182,8 +222,8 @@ def other_workloads(device, arith):
     t0 = time.perf_counter()
     run()
     dt = time.perf_counter() - t0
-    out["solo12_trot_B1024_from_centroidal_states (device-side problem builder)"] = {
-        "solves_per_s_e2e": B / dt, "ms": 1e3 * dt, "h2d_bytes": int(B * 8 * (9 + 12 + 1 + 3 + 1 + 2))}
+    out["solo12_trot_B1024_from_centroidal_states (device-side problem builder, e2e)"] = {
+        "solves_per_s": B / dt, "ms": 1e3 * dt, "h2d_bytes": int(B * 8 * (9 + 12 + 1 + 3 + 1 + 2))}
     s.close()
     # f-3: lock-step rollouts, one batched solve per replanning tick, step sizes carried, host-side plan builder and plant
     from bunmpc_b200.rollout import EpisodeState, LockstepRollouts, TrackingPlant
@@ -193,10 +233,25 @@ def other_workloads(device, arith):
     t0 = time.perf_counter()
     rec = roll.run(st, v_des, 0.0, n_ticks=6)
     dt = time.perf_counter() - t0
-    out["lockstep_rollouts_B1024_6_ticks (host plan builder + plant in the loop)"] = {
-        "solves_per_s_e2e": int((np.array([(r > 0).any(1).sum() for r in rec.iters])).sum()) / dt, "ms": 1e3 * dt,
+    out["lockstep_rollouts_B1024_6_ticks (host plan builder + plant in the loop, e2e)"] = {
+        "solves_per_s": int((np.array([(r > 0).any(1).sum() for r in rec.iters])).sum()) / dt, "ms": 1e3 * dt,
         "failed": int((rec.failed_at >= 0).sum())}
     return out
+
+
+def cpu_single_solve_latency(batch, n=96):
+    """p50 / p95 of ONE solve on ONE host core (the reference's own usage: one BiConvexMP::optimize per replan,
+    comparable to its dyn_time stamp, kino_dyn.cpp:46-48), over the first n instances of the workload."""
+    from oracle import oracle
+    lat = []
+    for i in range(min(n, batch.B)):
+        one = batch.select(np.arange(i, i + 1))
+        t0 = time.perf_counter()
+        oracle.solve(one, n_threads=1)
+        lat.append(time.perf_counter() - t0)
+    lat = np.array(lat) * 1e3
+    return {"p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)), "solves": int(len(lat)),
+            "cores": 1}
 
 
 def reference_arm(args, rank, world):
@@ -234,7 +289,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="instances per GPU per step")
-    ap.add_argument("--arith", default="strict", choices=["strict", "fma"])
+    ap.add_argument("--arith", default="strict", choices=["strict", "fma", "mixed"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     args = ap.parse_args()
@@ -250,45 +305,29 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from bunmpc_b200 import synthetic, ARITH_FMA, ARITH_STRICT
-    from bunmpc_b200.solver import BatchSolver
+    from bunmpc_b200 import synthetic, ARITH_FMA, ARITH_MIXED, ARITH_STRICT
+    from bunmpc_b200.dist import ShardedSolver
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    arith = ARITH_FMA if args.arith == "fma" else ARITH_STRICT
+    arith = {"strict": ARITH_STRICT, "fma": ARITH_FMA, "mixed": ARITH_MIXED}[args.arith]
     B = args.batch
 
-    # per-rank shard of the job: weak scaling, every GPU gets its own B perturbed states (seed = rank)
-    batch = synthetic.config(1, B=B, seed=rank)
-    solver = BatchSolver(batch.n_col, batch.n_eff, max_batch=B, device=local_rank)
-    dev = solver.upload(batch)
+    # ONE global batch of world * B perturbed states (the same on every rank), sharded interleaved: instance i -> rank
+    # i mod world.  Weak scaling: B instances per GPU at every N.
+    global_batch = synthetic.config(1, B=world * B, seed=0)
+    sharded = ShardedSolver(global_batch.n_col, global_batch.n_eff, shard_batch=B, device=local_rank)
+    dev = sharded.upload_global(global_batch)
+    batch = global_batch.shard(rank, world)
+    solver = sharded.solver
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    gathered = None
-    if world > 1:   # the path's only exchange step: gather the solved trajectories (NCCL over NVLink)
-        gathered = [torch.empty((world * B, solver.nf), dtype=torch.float64, device="cuda"),
-                    torch.empty((world * B, solver.nx), dtype=torch.float64, device="cuda")]
-
-    stats = torch.zeros(17, dtype=torch.float64, device="cuda")
 
     def step_resident():
-        out = solver.solve_resident(dev, arith=arith)
-        if world > 1:
-            # the path's only exchange steps (BASELINE.json): gather the solved trajectories and all-reduce the
-            # sufficient statistics of the Bayesian goal update (goal = desired velocity, error proxy = ||viol||)
-            dist.all_gather_into_tensor(gathered[0], out["F"])
-            dist.all_gather_into_tensor(gathered[1], out["X"])
-            g = dev.fields["X_ter"][:, 3:6]
-            e = torch.nan_to_num(out["viol"], nan=0.0)
-            stats[0] = float(g.shape[0])
-            stats[1:4] = g.sum(0)
-            stats[4:13] = (g[:, :, None] * g[:, None, :]).sum(0).reshape(9)
-            stats[13] = e.sum()
-            stats[14:17] = (e[:, None] * g).sum(0)
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-        return out
+        # the package's multi-GPU step: solve, fixed-order statistics kernel + all_reduce, all_gather of F and X
+        return sharded.step(arith=arith)
 
     def barrier():
         torch.cuda.synchronize()
@@ -339,7 +378,10 @@ def main():
         kt.append(a.elapsed_time(b) * 1e-3)
     k_time = float(np.mean(kt))
 
-    # ---- e2e: host-buffer C ABI call, pinned inputs/outputs, copies inside the timed region ----
+    # ---- e2e: host buffers in, host buffers out, every copy inside the timed region ----
+    # N = 1: the reference-facing C ABI call bunmpc_solve_compact_host (pinned inputs -> H2D -> kernels -> D2H).
+    # N > 1: each rank copies its pinned shard into the device batch, runs ShardedSolver.step (solve + statistics +
+    # NCCL gathers) and reads its results and the reduced statistics back.
     import ctypes as C
     from bunmpc_b200 import _lib
     pinned = {}
@@ -347,17 +389,32 @@ def main():
         a = getattr(batch, f)
         if a is None:
             continue
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        t = torch.from_numpy(np.ascontiguousarray(a.reshape(a.shape[0], -1))).pin_memory()
         pinned[f] = t
-        setattr(batch, f, t.numpy())
-    outbuf = {k: torch.empty(v.shape, dtype=torch.from_numpy(v).dtype).pin_memory().numpy() for k, v in out.items()}
+        setattr(batch, f, t.numpy().reshape(a.shape))
+    outbuf = {k: torch.empty(v.shape, dtype=torch.from_numpy(v).dtype).pin_memory() for k, v in out.items()}
+    outnp = {k: v.numpy() for k, v in outbuf.items()}
+    stats_host = torch.empty(17, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        if world == 1:
+            solver.solve(batch, arith=arith, out=outnp)
+            return
+        for f, t in pinned.items():
+            dev.fields[f].copy_(t, non_blocking=True)
+        o = sharded.step(arith=arith)
+        for k, v in outbuf.items():
+            v.copy_(o[k], non_blocking=True)
+        stats_host.copy_(sharded.stats, non_blocking=True)
+        torch.cuda.synchronize()
+
     for _ in range(2):
-        solver.solve(batch, arith=arith, out=outbuf)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(e2e_steps):
-        sol = solver.solve(batch, arith=arith, out=outbuf)
+        e2e_step()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
@@ -365,7 +422,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(te.item())
     h2d = batch.input_bytes()
-    d2h = int(sum(v.nbytes for v in outbuf.values()))
+    d2h = int(sum(v.numel() * v.element_size() for v in outbuf.values())) + (17 * 8 if world > 1 else 0)
 
     # ---- p50 latency of a single solve through the host API (B = 1) ----
     one = batch.select(np.arange(1))
@@ -376,6 +433,10 @@ def main():
         lat.append(time.perf_counter() - t0)
     p50_ms = float(np.median(lat[5:]) * 1e3)
 
+    # the other BASELINE configs at their real sizes (every rank takes part when world > 1)
+    others = None
+    if not args.no_extra:
+        others = other_workloads(local_rank, arith, world, rank)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -393,14 +454,17 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_ach = algorithmic_bytes(batch.n_col, B) / k_time * 1e-9
     info = solver.kernel_info()
+    ncu = ncu_constants()
+    traffic = ncu.get("dram_bytes_per_launch") if (ncu and B == 1024) else None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64" if args.arith != "mixed" else "f64 arithmetic, f32 storage of the Hessian / constraint rows",
+        "data": "synthetic",
         "config": {"workload": WORKLOAD, "instances_per_gpu_per_step": B, "n_col": batch.n_col, "n_eff": batch.n_eff,
                    "arith": args.arith, "l2": "flushed between steps (256 MiB write)",
-                   "sharding": "independent instances per rank, seed=rank" + (", nccl all_gather of F,X and all_reduce of 17 posterior statistics per step" if world > 1 else ""),
+                   "sharding": f"one global batch of {world * B} instances, instance i -> rank i mod {world}" + ("; per step: NCCL all_gather of F and X, all_reduce of 17 posterior statistics (bunmpc_b200.dist.ShardedSolver)" if world > 1 else ""),
                    "kernel": info},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -412,30 +476,31 @@ def main():
                        "converged_frac": float((out["status"] == 0).mean())},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak if fp64_peak else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch of this workload
-                     # (ncu --set full, profiles/r01_solve_kernel_s2_ncu_summary.txt); algorithmic: 10.9 MB
-                     "traffic": 13452544 if B == 1024 else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch of this workload, from
+                     # the ncu capture named in profiles/r02_ncu_constants.json; algorithmic: 10.9 MB
+                     "traffic": traffic,
                      "peak_source": "DFMA micro-benchmark measured in this run (bunmpc_measure_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 figure",
                      "kernel": "solve_kernel", "kernel_ms": 1e3 * k_time, "algorithmic_gflop_per_launch": flops * 1e-9},
-        # the busiest pipe (ncu): shared-memory data stage.  572 wavefronts per inner iteration (403 without bank
-        # conflicts) is the ncu count of the profiled launch of this same workload (profiles/r01_solve_kernel_s2_
-        # ncu_summary.txt: 57.8 % of peak); scaled here by the live iteration counters and the live kernel time.
-        "roofline_smem": smem_roofline(iters, k_time, clocks, info),
+        # the busiest memory pipe (ncu): shared-memory data stage; wavefronts per inner iteration from the ncu capture of
+        # this same workload, scaled by the live iteration counters and the live kernel time
+        "roofline_smem": smem_roofline(iters, k_time, clocks, info, ncu),
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_ach / hbm_peak,
-                         "traffic": 13452544 if B == 1024 else None,   # same ncu capture as roofline.traffic
+                         "traffic": traffic,   # same ncu capture as roofline.traffic
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
     }
-    # context legs run on rank 0 of a single-GPU run only (the other ranks of a multi-GPU run would just wait)
-    if not args.no_extra and world == 1:
-        line["other_workloads"] = other_workloads(local_rank, arith)
+    if others is not None:
+        line["other_workloads"] = others
+    # the CPU leg runs on rank 0 of a single-GPU run only (the other ranks of a multi-GPU run would just wait)
     if not args.no_cpu and world == 1:
         cores = cpu_cores()
-        v, n, dt = run_cpu(synthetic.config(1, B=B, seed=0), cores, B, budget_s=25.0)
+        cb = synthetic.config(1, B=B, seed=0)
+        v, n, dt = run_cpu(cb, cores, B, budget_s=20.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"first {n} instances of the same batch, {cores} threads, {dt:.1f} s, "
-                                          "oracle/bicon_oracle.c (gcc -O3), solve only"}
+                                          "oracle/bicon_oracle.c (gcc -O3), solve only",
+                                "single_solve_latency": cpu_single_solve_latency(cb)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -51,7 +51,7 @@ class Gait(C.Structure):
                 ("W_X_ter", C.c_double * 9), ("W_F", C.c_double * 12), ("rho", C.c_double)]
 
 
-STATE_FIELDS = ("com", "vcom", "amom", "foot_pos", "t", "v_des", "w_des", "cs_yaw", "amom_des", "scales")
+STATE_FIELDS = ("com", "vcom", "amom", "foot_pos", "t", "v_des", "w_des", "cs_yaw", "hip_xy", "amom_des", "scales")
 
 
 class States(C.Structure):
@@ -67,7 +67,7 @@ class Solution(C.Structure):
 EXPORTS = ("bunmpc_version", "bunmpc_last_error", "bunmpc_default_params", "bunmpc_create", "bunmpc_destroy",
            "bunmpc_launch_count", "bunmpc_kernel_info", "bunmpc_expand_device", "bunmpc_solve_expanded_device",
            "bunmpc_solve_compact_device", "bunmpc_build_problem_device", "bunmpc_solve_compact_host", "bunmpc_solve_expanded_host",
-           "bunmpc_centroidal_mats_host", "bunmpc_measure_fp64_peak", "bunmpc_selftest_division", "bunmpc_host_alloc", "bunmpc_host_free")
+           "bunmpc_goal_stats_device", "bunmpc_centroidal_mats_host", "bunmpc_measure_fp64_peak", "bunmpc_selftest_division", "bunmpc_host_alloc", "bunmpc_host_free")
 
 _lib = None
 
@@ -104,6 +104,7 @@ def lib():
                                             C.POINTER(Solution)]
     L.bunmpc_solve_expanded_host.argtypes = [C.c_void_p, C.POINTER(ExpandedProblem), C.POINTER(Params),
                                              C.POINTER(Solution)]
+    L.bunmpc_goal_stats_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(In), C.POINTER(In), C.c_void_p, C.c_void_p]
     L.bunmpc_centroidal_mats_host.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 9
     L.bunmpc_measure_fp64_peak.argtypes = [C.c_void_p, dp]
     L.bunmpc_selftest_division.argtypes = [C.c_void_p, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]

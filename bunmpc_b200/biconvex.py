@@ -166,9 +166,8 @@ class BiconvexMP:
 
     # ---- the solve ----
     def _get_solver(self):
-        if self._solver is None:
-            self._solver = get_solver(self.n_col_, self.n_eff_, 1, self.device)
-        return self._solver
+        # looked up on every use: the cache may have replaced (and closed) the handle when a larger batch arrived
+        return get_solver(self.n_col_, self.n_eff_, 1, self.device)
 
     def optimize(self, x_init, num_iters):
         """BiConvexMP::optimize, biconvex.cpp:80-120.  Runs on the GPU; iterates, dual and FISTA step sizes

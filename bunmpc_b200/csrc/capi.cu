@@ -310,20 +310,32 @@ int bunmpc_build_problem_device(bunmpc_solver *s, const bunmpc_gait *g, const bu
     if (!s || !g || !st || !x_init || !cnt_plan || !dt || !X_nom || !X_ter) return fail(BUNMPC_ERR_ARG, "build: null argument");
     if (st->batch < 1) return fail(BUNMPC_ERR_ARG, "build: batch < 1");
     if (!st->com.ptr || !st->vcom.ptr || !st->amom.ptr || !st->foot_pos.ptr || !st->t.ptr || !st->v_des.ptr ||
-        !st->w_des.ptr || !st->cs_yaw.ptr) return fail(BUNMPC_ERR_ARG, "build: null state field");
+        !st->w_des.ptr || (!st->cs_yaw.ptr && !st->hip_xy.ptr)) return fail(BUNMPC_ERR_ARG, "build: null state field");
     if (st->scales.ptr && (!W_X || !W_X_ter || !W_F || !rho)) return fail(BUNMPC_ERR_ARG, "build: scales need W_X, W_X_ter, W_F, rho outputs");
     if (s->e != 4) return fail(BUNMPC_ERR_UNSUPPORTED, "build: quadrupeds only");
     CK(cudaSetDevice(s->device));
     BuildArgs a;
     a.B = st->batch; a.n = s->n;
     a.com = mk(st->com); a.vcom = mk(st->vcom); a.amom = mk(st->amom); a.foot_pos = mk(st->foot_pos); a.t = mk(st->t);
-    a.v_des = mk(st->v_des); a.w_des = mk(st->w_des); a.cs_yaw = mk(st->cs_yaw); a.amom_des = mk(st->amom_des);
+    a.v_des = mk(st->v_des); a.w_des = mk(st->w_des); a.cs_yaw = mk(st->cs_yaw); a.hip_xy = mk(st->hip_xy); a.amom_des = mk(st->amom_des);
     a.scales = mk(st->scales);
     a.x_init = x_init; a.cnt_plan = cnt_plan; a.dt = dt; a.X_nom = X_nom; a.X_ter = X_ter;
     a.W_X = W_X; a.W_X_ter = W_X_ter; a.W_F = W_F; a.rho = rho;
     static_assert(sizeof(GaitDev) == sizeof(bunmpc_gait), "bunmpc_gait layout");
     memcpy(&a.g, g, sizeof(GaitDev));
     build_problem_kernel<<<(a.B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    s->launches++;
+    CK(cudaGetLastError());
+    return BUNMPC_OK;
+}
+
+int bunmpc_goal_stats_device(bunmpc_solver *s, int batch, const bunmpc_in *goals, const bunmpc_in *errors, double *out17,
+                             void *stream)
+{
+    if (!s || !goals || !errors || !goals->ptr || !errors->ptr || !out17 || batch < 1)
+        return fail(BUNMPC_ERR_ARG, "goal_stats: bad argument");
+    CK(cudaSetDevice(s->device));
+    goal_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(batch, mk(*goals), mk(*errors), out17);
     s->launches++;
     CK(cudaGetLastError());
     return BUNMPC_OK;

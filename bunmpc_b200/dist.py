@@ -27,8 +27,9 @@ def _dist():
     return dist
 
 
-def gather_solutions(local: BatchSolution, B: int, rank: int, world: int, device=None) -> BatchSolution:
-    """all_gather the per-rank results and undo the interleaved sharding: every rank gets the full batch."""
+def gather_solutions(local: BatchSolution, B: int, rank: int, world: int, device=None, m=None) -> BatchSolution:
+    """all_gather the per-rank results and undo the interleaved sharding: every rank gets the full batch.
+    m: the masses of the WHOLE batch ([B] or [1]); without it BatchSolution.mom() of the result raises."""
     import torch
     dist = _dist()
     per = (B + world - 1) // world                       # padded shard size
@@ -49,7 +50,7 @@ def gather_solutions(local: BatchSolution, B: int, rank: int, world: int, device
             idx = shard_indices(B, r, world)
             res[idx] = full[r, : len(idx)]
         out[name] = res.reshape((B,) + a.shape[1:])
-    return BatchSolution(m=None, **out)
+    return BatchSolution(m=m, **out)
 
 
 def solve_sharded(batch: CentroidalBatch, solve_fn: Callable[[CentroidalBatch], BatchSolution],
@@ -62,7 +63,92 @@ def solve_sharded(batch: CentroidalBatch, solve_fn: Callable[[CentroidalBatch], 
     local = solve_fn(batch.shard(rank, world))
     if not gather or world == 1:
         return local
-    return gather_solutions(local, batch.B, rank, world, device=device)
+    return gather_solutions(local, batch.B, rank, world, device=device, m=batch.m)
+
+
+class ShardedSolver:
+    """The multi-GPU step of the path, device resident: ONE global batch, sharded interleaved over the ranks
+    (instance i -> rank i % world), solved with no collective on the data path; afterwards the two exchange steps
+    BASELINE.json names run over NCCL on the same stream: all_gather of the solved trajectories (F, X) and all_reduce
+    of the 17 sufficient statistics of the Bayesian goal update (a fixed-order CUDA reduction of this rank's shard,
+    bunmpc_goal_stats_device).  Nothing touches host memory between upload and results.
+
+    One process per GPU (torchrun); with world == 1 the same code runs without the collectives."""
+
+    def __init__(self, n_col: int, n_eff: int = 4, shard_batch: int = 1024, device: int = 0):
+        import torch
+        import torch.distributed as dist
+        from .solver import BatchSolver
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.device = device
+        self.solver = BatchSolver(n_col, n_eff, max_batch=shard_batch, device=device)
+        self.shard_batch = shard_batch
+        dev = torch.device("cuda", device)
+        self.stats = torch.zeros(17, dtype=torch.float64, device=dev)
+        self._gathered = None
+        self.dev = None
+
+    def upload_global(self, batch: CentroidalBatch):
+        """Shard the global batch (identical on every rank) and put this rank's shard in HBM."""
+        local = batch.shard(self.rank, self.world)
+        self.global_B = batch.B
+        return self.upload_shard(local)
+
+    def upload_shard(self, local: CentroidalBatch):
+        import torch
+        if local.B > self.shard_batch:
+            raise ValueError("shard larger than the solver was created for")
+        self.dev = self.solver.upload(local)
+        self.local_B = local.B
+        dev = torch.device("cuda", self.device)
+        if self.world > 1:
+            # every rank holds ceil(B / world) rows in the gather buffers (the last ranks may own one instance less)
+            self._gathered = dict(
+                F=torch.zeros((self.world * self.shard_batch, self.solver.nf), dtype=torch.float64, device=dev),
+                X=torch.zeros((self.world * self.shard_batch, self.solver.nx), dtype=torch.float64, device=dev))
+        return self.dev
+
+    def step(self, params=None, arith=0, gather=True, stats=True, goals=None, errors=None):
+        """solve + (stats kernel, all_reduce) + (all_gather F, X), all asynchronous on torch's current stream.
+        goals: [B_local, 3] device tensor (default: the desired velocity of each instance, X_ter[:, 3:6]);
+        errors: [B_local] device tensor (default: the final dynamics violation).  Returns the local output dict."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        out = self.solver.solve_resident(self.dev, params=params, arith=arith)
+        if stats:
+            g = self.dev.fields["X_ter"] if goals is None else goals
+            e = out["viol"] if errors is None else errors
+            gin = (_lib.In(g.data_ptr() + 3 * 8, 0 if g.shape[0] == 1 else 9) if goals is None
+                   else _lib.In(g.data_ptr(), 3))
+            ein = _lib.In(e.data_ptr(), 1)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib().bunmpc_goal_stats_device(self.solver._h, int(self.local_B), C.byref(gin), C.byref(ein),
+                                                           C.c_void_p(self.stats.data_ptr()), C.c_void_p(stream)),
+                       "bunmpc_goal_stats_device")
+            if self.world > 1:
+                dist.all_reduce(self.stats, op=dist.ReduceOp.SUM)
+        if gather and self.world > 1:
+            nb = self.shard_batch
+            for k in ("F", "X"):
+                src = out[k] if out[k].shape[0] == nb else torch.nn.functional.pad(out[k], (0, 0, 0, nb - out[k].shape[0]))
+                dist.all_gather_into_tensor(self._gathered[k], src)
+        return out
+
+    def gathered(self, name: str, ordered: bool = True):
+        """The gathered trajectories of the last step() on this rank: [world * shard, width], rank-major; ordered=True
+        undoes the interleaved sharding (row i = instance i of the global batch, first global_B rows valid)."""
+        if self.world == 1:
+            return self.dev.out[name]
+        t = self._gathered[name]
+        if not ordered:
+            return t
+        w = t.shape[1]
+        return t.view(self.world, self.shard_batch, w).transpose(0, 1).reshape(self.world * self.shard_batch, w)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -46,7 +46,8 @@ class RobotConstants:
     foot_pos: np.ndarray          # [4,3] nominal foot positions (FL, FR, HL, HR) relative to the base xy, z on ground
     hip_offsets: np.ndarray       # [4,3] round(hip - com, 3) with the +-0.04 y shift, abstract_cyclic_gen.py:51-69
     foot_size: float = 0.018      # abstract_cyclic_gen.py:31
-    I_zz: float = 0.0             # composite inertia about yaw, used only when w_des != 0
+    I_zz: float = 0.0             # composite inertia about yaw, used only when w_des != 0.  AN INPUT: the reference reads it
+                                  # from pinocchio (crba, abstract_cyclic_gen.py:46-47); the defaults below are assumed values
     bx: float = 0.45              # abstract_cyclic_gen.py:92-97
     by: float = 0.45
     bz: float = 0.45
@@ -103,6 +104,24 @@ go2_trot = replace(solo12_trot, robot_name="go2", nom_ht=0.30)
 go2_bound = replace(solo12_bound, robot_name="go2", nom_ht=0.30)
 go2_jump = replace(solo12_jump, robot_name="go2", nom_ht=0.30)
 
+# NON-REFERENCE retuned Go2 set (SURVEY 8(d) config 3 allows one, "clearly labelled non-reference").  With the Solo12
+# records the reference algorithm itself does not converge for Go2's mass (the cone step of fista.cpp:59-67
+# compares a SQUARED tangential force with mu * f_z and diverges once forces exceed a few newtons; the penalty rho is
+# too weak against the cost weights for a 6x heavier robot; the exit test is absolute).  The retune keeps every rule of
+# the algorithm and changes three numbers, found with the CPU oracle: cost weights W_X, W_X_ter, W_F x 0.01 (rho / W
+# x 100), friction coefficient mu = 200 (the squared-norm cone then only cuts in above ~90 N of tangential force per
+# foot), exit tolerance 6e-3 = 1e-3 x the mass ratio.  Trot: 97 % of perturbed instances converge (38 outer iterations
+# on average), bound 88 %; the jump gait still does not.
+GO2_RETUNE_WEIGHT_SCALE = 0.01
+GO2_RETUNE_SOLVER = dict(mu=200.0, exit_tol=6e-3)
+
+
+def _retuned(p):
+    return replace(p, robot_name="go2_retuned", W_X=p.W_X * GO2_RETUNE_WEIGHT_SCALE,
+                   W_X_ter=p.W_X_ter * GO2_RETUNE_WEIGHT_SCALE, W_F=p.W_F * GO2_RETUNE_WEIGHT_SCALE)
+
+
 GAITS = {"solo12": {"trot": solo12_trot, "bound": solo12_bound, "jump": solo12_jump},
-         "go2": {"trot": go2_trot, "bound": go2_bound, "jump": go2_jump}}
-ROBOTS = {"solo12": SOLO12, "go2": GO2}
+         "go2": {"trot": go2_trot, "bound": go2_bound, "jump": go2_jump},
+         "go2_retuned": {"trot": _retuned(go2_trot), "bound": _retuned(go2_bound), "jump": _retuned(go2_jump)}}
+ROBOTS = {"solo12": SOLO12, "go2": GO2, "go2_retuned": GO2}

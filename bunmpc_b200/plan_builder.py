@@ -22,12 +22,27 @@ def _b(a, B, tail):
     return np.broadcast_to(a, (B,) + tuple(tail)).copy()
 
 
+def rotated_hip_offsets(robot: RobotConstants, yaw):
+    """(R hip_offset_j)[0:2] of abstract_cyclic_gen.py:279,347 with R = rpyToMatrix(0, 0, yaw), formed with numpy.matmul
+    exactly as the reference forms it (its rounding is the BLAS's, typically fused); [B,e,2]."""
+    yaw = np.atleast_1d(np.asarray(yaw, dtype=np.float64))
+    out = np.zeros((yaw.shape[0], len(robot.eff_names), 2))
+    for b, y in enumerate(yaw):
+        cy, sy = np.cos(y), np.sin(y)
+        R = np.array([[cy, -sy, 0.0], [sy, cy, 0.0], [0.0, 0.0, 1.0]])
+        for j in range(out.shape[1]):
+            out[b, j] = np.matmul(R, np.asarray(robot.hip_offsets[j], dtype=np.float64))[0:2]
+    return out
+
+
 def build_contact_plan(robot: RobotConstants, params: BiconvexMotionParams, com, foot_pos, t, v_des, w_des,
-                       yaw=0.0, horizon=None):
+                       yaw=0.0, horizon=None, hip_xy=None):
     """create_cnt_plan, abstract_cyclic_gen.py:159-414 (height_map=None, noise_std=None, mcts=None).
 
     com [B,3], foot_pos [B,e,3] (current end-effector positions; rounded to 3 dp as :211/:240 unless they
     are given as ee_pos), t [B], v_des [B,3] (already in the local frame, :642-643), w_des [B], yaw [B].
+    hip_xy [B,e,2]: the rotated hip offsets (R hip_offset_j)[0:2]; None = cos/sin(yaw) products, unfused (what the CUDA
+    builder computes when it is not handed the products either).
     Returns cnt_plan [B,n,e,4], dt [B,n]."""
     com = np.atleast_2d(np.asarray(com, dtype=np.float64))
     B = com.shape[0]
@@ -62,7 +77,8 @@ def build_contact_plan(robot: RobotConstants, params: BiconvexMotionParams, com,
             stance = gp.get_phase(ft, j) == 1                          # :263
             prev_stance = cnt_plan[:, i - 1, j, 0] == 1                # :269
             off = robot.hip_offsets[j]
-            rot_off = np.stack([cy * off[0] - sy * off[1], sy * off[0] + cy * off[1]], axis=1)
+            rot_off = (np.stack([cy * off[0] - sy * off[1], sy * off[0] + cy * off[1]], axis=1) if hip_xy is None
+                       else _b(hip_xy, B, (e, 2))[:, j])
             hip_loc = com_xy + rot_off + i * gait_dt * vtrack          # :279,347
             raibert = 0.5 * vtrack * params.gait_period * params.stance_percent[j] \
                 - 0.05 * (vtrack - v_des[:, 0:2])                      # :282
@@ -121,14 +137,15 @@ def build_costs(robot: RobotConstants, params: BiconvexMotionParams, x_init, dt,
 
 def build_batch(robot: RobotConstants, params: BiconvexMotionParams, com, vcom, amom, foot_pos, t, v_des, w_des,
                 yaw=0.0, amom_des=None, horizon=None, L0=None, scale_W_X=None, scale_W_F=None,
-                scale_rho=None) -> CentroidalBatch:
+                scale_rho=None, hip_xy=None) -> CentroidalBatch:
     """One CentroidalBatch from centroidal states: contact plan + costs + bounds.  The optional per-instance
     scalings multiply W_X / W_X_ter, W_F and rho (BASELINE config 5's cost-weight samples)."""
     com = np.atleast_2d(np.asarray(com, dtype=np.float64))
     B = com.shape[0]
     x_init = np.concatenate([com, _b(vcom, B, (3,)), _b(amom, B, (3,))], axis=1)
     v_des = _b(v_des, B, (3,))
-    cnt_plan, dt = build_contact_plan(robot, params, com, foot_pos, t, v_des, w_des, yaw=yaw, horizon=horizon)
+    cnt_plan, dt = build_contact_plan(robot, params, com, foot_pos, t, v_des, w_des, yaw=yaw, horizon=horizon,
+                                      hip_xy=hip_xy)
     W_X, W_X_ter, X_nom, X_ter, W_F, bounds = build_costs(robot, params, x_init, dt, v_des, w_des, amom_des)
     rho = np.array([params.rho], dtype=np.float64)
     if scale_W_X is not None:

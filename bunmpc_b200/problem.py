@@ -146,6 +146,8 @@ class BatchSolution:
 
     def mom(self):
         """return_opt_mom, biconvex.cpp:132-142: [B, n+1, 6] = [m*vcom, amom]"""
+        if self.m is None:
+            raise ValueError("BatchSolution.mom(): the masses of the batch are not known (pass m to gather_solutions)")
         Xr = self.X.reshape(self.X.shape[0], -1, 9)
         m = np.broadcast_to(np.asarray(self.m, dtype=np.float64).reshape(-1, 1, 1), (Xr.shape[0], 1, 1))
         return np.concatenate([m * Xr[:, :, 3:6], Xr[:, :, 6:9]], axis=2)

@@ -123,7 +123,8 @@ class LockstepRollouts:
                 break
             st = state.select(idx)
             batch = build_batch(self.robot, self.params, st.com, st.vcom, st.amom, st.foot_pos, st.t, v_des[idx],
-                                w_des[idx], yaw=st.yaw, amom_des=amom_des, horizon=self.horizon,
+                                w_des[idx], yaw=st.yaw, horizon=self.horizon,
+                                amom_des=(amom_des if amom_des is None or np.ndim(amom_des) < 2 else np.asarray(amom_des)[idx]),
                                 L0=None if L is None else L[idx])
             sol = self._solve(batch)
             if L is None:

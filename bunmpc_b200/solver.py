@@ -204,7 +204,7 @@ class BatchSolver:
         return DeviceBatch(B=B, fields=fields, out=out, widths=w)
 
     def build_device(self, robot, params, com, vcom, amom, foot_pos, t, v_des, w_des, yaw=0.0, amom_des=None,
-                     scales=None, L0=None) -> DeviceBatch:
+                     scales=None, L0=None, hip_xy=None) -> DeviceBatch:
         """Batched problem builder ON THE DEVICE: contact plan (create_cnt_plan,
         abstract_cyclic_gen.py:159-414) and nominal/terminal references (create_costs, :564-614) from centroidal
         states; only the states cross PCIe.  Same results, bit for bit, as plan_builder.build_batch (numpy)."""
@@ -226,6 +226,7 @@ class BatchSolver:
         st_t = dict(com=up(com, (3,)), vcom=up(vcom, (3,)), amom=up(amom, (3,)), foot_pos=up(foot_pos, (e, 3)),
                     t=up(t, ()), v_des=up(v_des, (3,)), w_des=up(w_des, ()),
                     cs_yaw=up(np.stack([np.cos(yaw), np.sin(yaw)], axis=1), (2,)),
+                    hip_xy=None if hip_xy is None else up(hip_xy, (e, 2)),
                     amom_des=None if amom_des is None else up(amom_des, (3,)),
                     scales=None if scales is None else up(scales, (3,)))
         g = _lib.Gait()
@@ -243,7 +244,7 @@ class BatchSolver:
             g.W_F[k] = params.W_F[k]
         st = _lib.States()
         st.batch = B
-        widths = dict(com=3, vcom=3, amom=3, foot_pos=3 * e, t=1, v_des=3, w_des=1, cs_yaw=2, amom_des=3, scales=3)
+        widths = dict(com=3, vcom=3, amom=3, foot_pos=3 * e, t=1, v_des=3, w_des=1, cs_yaw=2, hip_xy=2 * e, amom_des=3, scales=3)
         for f in _lib.STATE_FIELDS:
             tt = st_t[f]
             setattr(st, f, _lib.In(None, 0) if tt is None else _lib.In(tt.data_ptr(), widths[f]))

@@ -120,7 +120,10 @@ long long bunmpc_launch_count(const bunmpc_solver *s);
 int  bunmpc_kernel_info(const bunmpc_solver *s, int *ctas_per_sm, int *threads, int *smem_bytes, int *num_sms);
 
 /* ---- device-pointer entry points: asynchronous on `stream` (a cudaStream_t; NULL = CUDA's default stream).
- *      All pointers in the structs are device pointers on the solver's device. ---- */
+ *      All pointers in the structs are device pointers on the solver's device.
+ *      ONE solve in flight per handle: the work queue, the parked states of the time slicing and the expanded problem
+ *      are scratch of the handle, so a second solve on the same handle has to be ordered after the first (same stream,
+ *      or an event); use one handle per concurrent stream. ---- */
 
 /* create_bound_constraints + create_cost_X + create_cost_F for a batch (biconvex.cpp:27-78):
  * writes Qx,qx,lbx,ubx [B][nx] and Qf,qf [B][nf]. */
@@ -156,7 +159,11 @@ typedef struct {
     bunmpc_in t;                   /* [B] time inside the gait (replanning phase) */
     bunmpc_in v_des;               /* [B][3] desired velocity, already in the local frame (:642-643) */
     bunmpc_in w_des;               /* [B] */
-    bunmpc_in cs_yaw;              /* [B][2] cos and sin of the base yaw (R of :172-177) */
+    bunmpc_in cs_yaw;              /* [B][2] cos and sin of the base yaw (R of :172-177); unused when hip_xy is given */
+    bunmpc_in hip_xy;              /* [B][4][2] (R hip_offset_j)[0:2], the rotated hip offsets of :279,347.  The reference
+                                      forms them with numpy.matmul, whose rounding depends on the BLAS numpy is linked
+                                      with, so a caller that wants the reference's bits passes the products themselves;
+                                      ptr NULL = cos(yaw) ox - sin(yaw) oy, sin(yaw) ox + cos(yaw) oy, unfused */
     bunmpc_in amom_des;            /* [B][3] log3(R_des R_q^T) (:616-627); ptr NULL = 0 */
     bunmpc_in scales;              /* [B][3] multipliers of (W_X and W_X_ter, W_F, rho); ptr NULL = none */
 } bunmpc_states;
@@ -166,6 +173,14 @@ typedef struct {
 int bunmpc_build_problem_device(bunmpc_solver *s, const bunmpc_gait *g, const bunmpc_states *st, double *x_init,
                                 double *cnt_plan, double *dt, double *X_nom, double *X_ter, double *W_X,
                                 double *W_X_ter, double *W_F, double *rho, void *stream);
+
+/* Sufficient statistics of the Bayesian goal update over one rank's shard (the reference's grid posterior with a Gaussian
+ * likelihood centred at the sampled goal, locosafedagger_modified.py:357-402): goals [B][3] (batch stride in elements,
+ * e.g. the desired velocity X_ter + 3 with stride 9), errors [B] (NaN counts as 0) -> out17 = [N, sum g (3),
+ * sum g g^T (9), sum e, sum e g (3)], device pointers, asynchronous on `stream`, fixed summation order.  The 17 doubles
+ * are what the ranks of a multi-GPU job all-reduce (NCCL). */
+int bunmpc_goal_stats_device(bunmpc_solver *s, int batch, const bunmpc_in *goals, const bunmpc_in *errors, double *out17,
+                             void *stream);
 
 /* ---- host-pointer entry points: copy in, solve, copy out, synchronise.  Pointers are host pointers
  *      (pinned memory makes the copies asynchronous).  This is what the python BiconvexMP calls. ---- */

@@ -1,0 +1,13 @@
+"""Stand-in for robot_properties_solo.config (TEST INFRASTRUCTURE ONLY, oracle/pinshim/README.md): the reference's
+motion files (examples/motions/cyclic/solo12_*.py) call Solo12Config.buildRobotWrapper() at import time and read
+model.nv from it."""
+import pinocchio as pin
+
+
+class Solo12Config:
+    urdf_path = "solo12.urdf"
+    mass = 2.5          # sum of <mass> in robots/solo12/urdf/solo12.urdf
+
+    @classmethod
+    def buildRobotWrapper(cls):
+        return pin.FakeRobot(cls.mass, nv=18)

@@ -26,5 +26,6 @@ cyc = o["cycles"].cpu().numpy()
 inner = it[:, 1] + it[:, 2]
 info = s.kernel_info()
 per_sm = inner.sum() / info["num_sms"]
+print(f"total inner iterations of one launch: {int(inner.sum())}")
 print(f"B={B} n={b.n_col} max_outer={mo} arith={arith}: {dt*1e3:.2f} ms, {B/dt:.0f} solves/s, inner F/X mean {it[:,1].mean():.0f}/{it[:,2].mean():.0f}, "
       f"cycles per inner iteration per CTA {cyc.sum()/inner.sum():.0f}, SM cycles per inner iteration {dt*1.965e9/per_sm:.0f}, kernel {info}")

@@ -1,0 +1,85 @@
+"""The batched problem builder against the reference's OWN python: tests/golden/plan_cases.npz holds what
+examples/mpc/abstract_cyclic_gen.py (create_cnt_plan :159-414, create_costs :532-614, imported in place, pinocchio and
+the pybind modules replaced by oracle/pinshim, phase lookup by the reference's own gait_planner.cpp) handed to its
+solver on 36 cases: three gaits, both robots' masses, times on and off the planning grid and on phase edges, yaw over the
+full circle, roll/pitch, turning (w_des != 0), overridden horizons.  Bit for bit."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from tests.golden.make_plan_golden import load
+
+CASES, MOTIONS = load()
+
+
+def _robot_and_params(d):
+    from bunmpc_b200 import motions
+    prm = motions.GAITS["solo12"][d["gait"]]
+    robot = dataclasses.replace(motions.SOLO12, mass=float(d["mass"]), hip_offsets=d["hip_offsets"], I_zz=float(d["I_zz"]))
+    return robot, prm
+
+
+def test_motion_records_equal_the_reference_files():
+    """bunmpc_b200/motions.py was transcribed from examples/motions/cyclic/solo12_{trot,bound,jump}.py; the golden file
+    carries the records those files define when imported."""
+    from bunmpc_b200 import motions
+    for gait, rec in MOTIONS.items():
+        prm = motions.GAITS["solo12"][gait]
+        for k, v in rec.items():
+            assert np.array_equal(np.asarray(getattr(prm, k), dtype=np.float64), v), (gait, k)
+        assert prm.horizon() == int(np.round(rec["gait_horizon"] * rec["gait_period"] / rec["gait_dt"], 2))
+
+
+@pytest.mark.parametrize("name,d", CASES, ids=[c[0] for c in CASES])
+def test_host_builder_equals_reference_python(name, d):
+    from bunmpc_b200 import plan_builder
+    robot, prm = _robot_and_params(d)
+    b = plan_builder.build_batch(robot, prm, d["com"][None], d["vcom"][None], d["amom"][None], d["foot_pos"][None],
+                                 d["t"][None], d["v_des"][None], d["w_des"][None], yaw=d["yaw"][None],
+                                 amom_des=d["amom_des"][None], horizon=int(d["horizon"]), hip_xy=d["hip_xy"][None])
+    n = int(d["horizon"])
+    assert b.n_col == n
+    assert np.array_equal(b.cnt_plan[0], d["cnt_plan"]), "cnt_plan"
+    assert np.array_equal(b.dt[0], d["dt"]), "dt"
+    assert np.array_equal(b.x_init[0], d["x_init"]), "x_init"
+    assert np.array_equal(b.X_nom[0], d["X_nom"]), "X_nom"
+    assert np.array_equal(b.X_ter[0], d["X_ter"]), "X_ter"
+    assert np.array_equal(np.broadcast_to(b.W_X, (1, 9 * n))[0], d["W_X"])
+    assert np.array_equal(np.broadcast_to(b.W_X_ter, (1, 9))[0], d["W_X_ter"])
+    assert np.array_equal(np.broadcast_to(b.W_F, (1, 12 * n))[0], d["W_F"])
+    assert np.array_equal(np.broadcast_to(b.bounds, (1, n, 6))[0], d["bounds"])
+    assert float(np.ravel(b.rho)[0]) == float(d["rho"])
+
+
+@pytest.mark.gpu
+def test_device_builder_equals_reference_python():
+    """build_problem_kernel (one launch per group of cases with the same gait and horizon) == the reference's python."""
+    from bunmpc_b200.solver import BatchSolver
+    groups = {}
+    for name, d in CASES:
+        groups.setdefault((d["gait"], int(d["horizon"]), float(d["mass"])), []).append(d)
+    checked = 0
+    for (gait, n, mass), ds in groups.items():
+        s = BatchSolver(n, 4, max_batch=len(ds))
+        for d in ds:     # hip offsets / yaw inertia differ per case (they come from the injected robot): one launch each
+            robot, prm = _robot_and_params(d)
+            if prm.horizon() != n:
+                prm = dataclasses.replace(prm, gait_horizon=n * prm.gait_dt / prm.gait_period)
+                assert prm.horizon() == n
+            dev = s.build_device(robot, prm, d["com"][None], d["vcom"][None], d["amom"][None], d["foot_pos"][None],
+                                 d["t"][None], d["v_des"][None], d["w_des"][None], yaw=d["yaw"][None],
+                                 amom_des=d["amom_des"][None], hip_xy=d["hip_xy"][None])
+            f = {k: v.cpu().numpy() for k, v in dev.fields.items() if v is not None}
+            assert np.array_equal(f["cnt_plan"][0], d["cnt_plan"].reshape(-1)), (gait, "cnt_plan")
+            assert np.array_equal(f["dt"][0], d["dt"]) and np.array_equal(f["x_init"][0], d["x_init"])
+            if prm.horizon() == motions_horizon(gait):      # X_ter uses gait_horizon itself (:593)
+                assert np.array_equal(f["X_ter"][0], d["X_ter"]), (gait, "X_ter")
+            assert np.array_equal(f["X_nom"][0], d["X_nom"]), (gait, "X_nom")
+            checked += 1
+    assert checked == len(CASES)
+
+
+def motions_horizon(gait):
+    from bunmpc_b200 import motions
+    return motions.GAITS["solo12"][gait].horizon()
