@@ -1,0 +1,76 @@
+"""NCCL test of the shipped multi-GPU step (bunmpc_b200.dist.ShardedSolver): two ranks on two GPUs, one global batch
+sharded interleaved, all_gather of the trajectories and all_reduce of the posterior statistics on the device.  Needs two
+visible GPUs (skipped otherwise); the single-GPU variant below checks the same code path with world = 1."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+B = 37            # odd on purpose: the ranks own 19 and 18 instances
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from bunmpc_b200 import SolverParams, synthetic
+    from bunmpc_b200.dist import ShardedSolver
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    batch = synthetic.perturbed(B, seed=4)
+    sh = ShardedSolver(batch.n_col, batch.n_eff, shard_batch=(B + world - 1) // world, device=rank)
+    sh.upload_global(batch)
+    sh.step(params=SolverParams(max_outer=4))
+    torch.cuda.synchronize()
+    q.put((rank, sh.gathered("F").cpu().numpy()[:B], sh.gathered("X").cpu().numpy()[:B], sh.stats.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _expected(oracle):
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.dist import goal_sufficient_stats
+    batch = synthetic.perturbed(B, seed=4)
+    ref = oracle.solve(batch, params=oracle.default_params(max_outer=4), n_threads=8)
+    stats = goal_sufficient_stats(batch.X_ter[:, 3:6], np.nan_to_num(ref["viol"], nan=0.0))
+    return ref, stats
+
+
+def test_sharded_step_two_gpus_nccl(oracle):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world, port = 2, 29700 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref, stats = _expected(oracle)
+    for rank, F, X, st in res:
+        assert np.array_equal(F, ref["F"]) and np.array_equal(X, ref["X"]), rank       # every rank holds the whole batch
+        assert st[0] == B and np.allclose(st, stats, rtol=1e-12, atol=1e-15), rank
+
+
+def test_sharded_step_single_gpu(oracle):
+    """world = 1: same step, no collectives; the statistics kernel against numpy."""
+    from bunmpc_b200 import SolverParams, synthetic
+    from bunmpc_b200.dist import ShardedSolver
+    batch = synthetic.perturbed(B, seed=4)
+    sh = ShardedSolver(batch.n_col, batch.n_eff, shard_batch=B, device=0)
+    sh.upload_global(batch)
+    o = sh.step(params=SolverParams(max_outer=4))
+    ref, stats = _expected(oracle)
+    assert np.array_equal(o["F"].cpu().numpy(), ref["F"]) and np.array_equal(sh.gathered("X").cpu().numpy(), ref["X"])
+    st = sh.stats.cpu().numpy()
+    assert st[0] == B and np.allclose(st, stats, rtol=1e-12, atol=1e-15)
