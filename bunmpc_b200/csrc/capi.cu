@@ -266,6 +266,10 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     else if (smem != s->smem_bytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, s->nthreads, smem));
     if (per_sm < 1) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: kernel does not fit on an SM");
     long long grid = (long long)s->num_sms * per_sm;
+    if (const char *ev = getenv("BUNMPC_MAX_CTAS")) {   // test knob: few resident CTAs, so that a handful of instances exercises the time slicing
+        const long long cap = atoll(ev);
+        if (cap >= 1 && cap < grid) grid = cap;
+    }
     if (grid > a.B) grid = a.B;
     // time slicing: with more instances than resident CTAs, park an instance after a few outer iterations so that
     // the launch ends on a short slice instead of on the longest instance (iteration counts spread 4x)
