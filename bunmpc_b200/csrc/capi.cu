@@ -255,7 +255,7 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     solve_fn fn = solve_pick(s->nthreads, prm->arith);
     int per_sm = s->ctas_per_sm[prm->arith];
     if (const char *ev = getenv("BUNMPC_CTAS")) {      // experiment: occupancy variants of the 96-thread MIXED kernel
-        solve_fn alt = (s->nthreads == 96 && prm->arith == 2) ? solve_inst_x96(2, atoi(ev)) : nullptr;
+        solve_fn alt = (s->nthreads == 96) ? solve_inst_x96(prm->arith, atoi(ev)) : nullptr;
         if (alt) {
             fn = alt;
             CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));

@@ -11,17 +11,21 @@
 
 namespace bunmpc {
 
-#define BUNMPC_MINB_OF(NT, MINB) NT == INST_NT ? MINB:
-constexpr int kMinBlocks = BUNMPC_NT_LIST(BUNMPC_MINB_OF) 1;
+#define BUNMPC_MAXREG_OF(NT, MAXREG) NT == INST_NT ? MAXREG:
+constexpr int kMaxReg = BUNMPC_NT_LIST(BUNMPC_MAXREG_OF) 1;
 
-solve_fn INST_NAME() { return solve_kernel<4, INST_ARITH, INST_NT, kMinBlocks>; }
+solve_fn INST_NAME() { return solve_kernel<4, INST_ARITH, INST_NT, kMaxReg>; }
 
-#if INST_NT == 96 && INST_ARITH == 2
-solve_fn solve_inst_x96(int arith, int ctas)
+#if INST_NT == 96
+// occupancy variants of the 96-thread kernel (BUNMPC_CTAS in the environment, see capi.cu): 4 CTAs per SM at 168
+// registers, 5 at 136 (only the MIXED mode's binary32 rows make that worthwhile)
+#define INST_X96_NAME INST_CAT(solve_inst_x, INST_NT, INST_ARITH)
+solve_fn INST_X96_NAME(int ctas)
 {
-    (void)arith;
-    if (ctas == 5) return solve_kernel<4, 2, 96, 5>;
-    if (ctas == 6) return solve_kernel<4, 2, 96, 6>;
+    if (ctas == 4) return solve_kernel<4, INST_ARITH, 96, 168>;
+#if INST_ARITH == 2
+    if (ctas == 5) return solve_kernel<4, 2, 96, 136>;
+#endif
     return nullptr;
 }
 #endif

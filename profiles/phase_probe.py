@@ -18,7 +18,7 @@ b = synthetic.config(1, B=B, seed=0)
 s = BatchSolver(b.n_col, b.n_eff, max_batch=B)
 sol = s.solve(b, viol_hist=True)       # profiling build: the viol_hist buffer of each instance carries 32 counters
 tr = sol.viol_hist.view(np.int64).reshape(-1)[: B * 32].reshape(B, 32).astype(np.float64)
-names = ["rest of phase 1 (F: row sums of y_k)", "barrier 1", "phase 2", "barrier 2", "decision", "loads+gradient", "division", "projection", "sums+momentum"]
+names = ["leaves/stores/shift (X: after prox)", "barrier", "-", "-", "-", "totals+decision (F: +rows)", "gradient (X: +rows)", "warp tree", "prox (X: +leaves)"]
 for prob, pn, itc in ((0, "F", sol.iters[:, 1]), (1, "X", sol.iters[:, 2])):
     per = tr[:, 16 * prob: 16 * prob + 9].sum(0) / itc.sum()
     print(f"B={B} {pn} cycles per inner iteration (thread 0): " + "  ".join(f"{n} {v:6.0f}" for n, v in zip(names, per))
