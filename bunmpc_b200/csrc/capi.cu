@@ -254,8 +254,8 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     if (smem > kMaxSmemBytes) return fail(BUNMPC_ERR_UNSUPPORTED, "solve: shared memory need exceeds one SM");
     solve_fn fn = solve_pick(s->nthreads, prm->arith);
     int per_sm = s->ctas_per_sm[prm->arith];
-    if (const char *ev = getenv("BUNMPC_CTAS")) {      // experiment: occupancy variants of the 96-thread MIXED kernel
-        solve_fn alt = (s->nthreads == 96) ? solve_inst_x96(prm->arith, atoi(ev)) : nullptr;
+    if (const char *ev = getenv("BUNMPC_CTAS")) {      // experiment: occupancy variant of the 128-thread kernel
+        solve_fn alt = (s->nthreads == 128) ? solve_inst_x128(prm->arith, atoi(ev)) : nullptr;
         if (alt) {
             fn = alt;
             CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));

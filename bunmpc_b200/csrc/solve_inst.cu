@@ -16,16 +16,13 @@ constexpr int kMaxReg = BUNMPC_NT_LIST(BUNMPC_MAXREG_OF) 1;
 
 solve_fn INST_NAME() { return solve_kernel<4, INST_ARITH, INST_NT, kMaxReg>; }
 
-#if INST_NT == 96
-// occupancy variants of the 96-thread kernel (BUNMPC_CTAS in the environment, see capi.cu): 4 CTAs per SM at 168
-// registers, 5 at 136 (only the MIXED mode's binary32 rows make that worthwhile)
-#define INST_X96_NAME INST_CAT(solve_inst_x, INST_NT, INST_ARITH)
-solve_fn INST_X96_NAME(int ctas)
+#if INST_NT == 128
+// occupancy variant of the 128-thread kernel (BUNMPC_CTAS=3 in the environment, see capi.cu): 3 CTAs per SM at 168
+// registers instead of 2 at 255
+#define INST_X128_NAME INST_CAT(solve_inst_x, INST_NT, INST_ARITH)
+solve_fn INST_X128_NAME(int ctas)
 {
-    if (ctas == 4) return solve_kernel<4, INST_ARITH, 96, 168>;
-#if INST_ARITH == 2
-    if (ctas == 5) return solve_kernel<4, 2, 96, 136>;
-#endif
+    if (ctas == 3) return solve_kernel<4, INST_ARITH, 128, 168>;
     return nullptr;
 }
 #endif

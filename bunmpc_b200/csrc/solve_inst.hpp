@@ -8,24 +8,27 @@ namespace bunmpc {
 
 typedef void (*solve_fn)(const SolveArgs);
 
-// Threads per CTA -> registers per thread (__maxnreg__).  The pipelined FISTA loops keep two Hessian rows per variable,
-// the iterate triples and the sums in flight in registers and want ~224 of them without spilling: an SM (64K registers)
-// then holds 288 solver threads: 3 CTAs of 96, 2 of 128, 1 of 192/256.  From 384 threads on the budget shrinks
-// (168 / 128 / 80 / 64 registers) and the Hessian rows spill to local memory.
-#define BUNMPC_NT_LIST(X) X(32, 255) X(64, 255) X(96, 255) X(128, 255) X(192, 255) X(256, 255) X(384, 168) X(512, 128) X(768, 80) X(1024, 64)
-// occupancy variants of the 96-thread kernel (BUNMPC_CTAS=4|5 in the environment, see capi.cu)
-solve_fn solve_inst_x96_0(int ctas);
-solve_fn solve_inst_x96_1(int ctas);
-solve_fn solve_inst_x96_2(int ctas);
-inline solve_fn solve_inst_x96(int arith, int ctas)
+// Threads per CTA -> registers per thread (__maxnreg__).  A CTA is the worker warps that own the variables plus one
+// service warp (kernels.cuh).  The pipelined FISTA loops keep the Hessian rows, the constraint rows, the iterate triples
+// and the sums in flight in registers and want ~250 of them; a scheduler (16K registers) then holds two warps, an SM
+// eight: 2 CTAs of 128 threads (the trot horizon), 1 of 256.  From 384 threads on the budget shrinks
+// (168 / 128 / 80 / 64 registers) and rows move to shared-memory records or spill.
+#define BUNMPC_NT_LIST(X) X(64, 255) X(96, 255) X(128, 255) X(160, 255) X(192, 255) X(256, 255) X(384, 168) X(512, 128) X(768, 80) X(1024, 64)
+// occupancy variant of the 128-thread kernel (BUNMPC_CTAS=3 in the environment, see capi.cu)
+solve_fn solve_inst_x128_0(int ctas);
+solve_fn solve_inst_x128_1(int ctas);
+solve_fn solve_inst_x128_2(int ctas);
+inline solve_fn solve_inst_x128(int arith, int ctas)
 {
-    return arith == 2 ? solve_inst_x96_2(ctas) : (arith ? solve_inst_x96_1(ctas) : solve_inst_x96_0(ctas));
+    return arith == 2 ? solve_inst_x128_2(ctas) : (arith ? solve_inst_x128_1(ctas) : solve_inst_x128_0(ctas));
 }
 
-// smallest CTA size that holds a horizon: e*n force threads and 3(n+1) state/row threads
+// smallest CTA size that holds a horizon: e*n force threads and 3(n+1) state/row threads in the worker warps, plus the
+// service warp
 inline int solve_threads(int n, int e)
 {
-    const int need = (e * n > 3 * (n + 1)) ? e * n : 3 * (n + 1);
+    const int work = (e * n > 3 * (n + 1)) ? e * n : 3 * (n + 1);
+    const int need = 32 * ((work + 31) / 32) + 32;
 #define BUNMPC_PICK_NT(NT, MAXREG) if (need <= NT) return NT;
     BUNMPC_NT_LIST(BUNMPC_PICK_NT)
 #undef BUNMPC_PICK_NT
