@@ -1,5 +1,7 @@
 """GPU parity tests proper: the CUDA path through the C ABI against the CPU oracle, bit for bit
 (integer counters and IEEE binary64 values identical), on the same seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -203,3 +205,53 @@ def test_mixed_mode_matches_its_oracle_and_the_tolerance(oracle):
     assert same.mean() > 0.8
     assert r_sc.max() <= 1e-3       # north star: within 1e-3 relative in FP32 mode
     assert np.median(r_c) <= 1e-6
+
+
+@pytest.mark.parametrize("cfg,per_gpu", [(2, 2048), (3, 512), (4, 8192)])
+def test_per_gpu_shard_sizes_sampled(oracle, cfg, per_gpu):
+    """BASELINE configs 3-5 at the size ONE of eight GPUs sees (16 384 / 4 096 / 65 536 instances sharded interleaved):
+    many more instances than CTA slots, so every instance is parked and resumed several times and the work queue is under
+    pressure.  The GPU solves the whole shard; the oracle re-solves 256 randomly drawn instances, bit for bit."""
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.solver import BatchSolver
+    full = synthetic.config(cfg, B=8 * per_gpu, seed=5)
+    b = full.shard(3, 8)
+    assert b.B == per_gpu
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=per_gpu).solve(b)
+    idx = np.sort(np.random.default_rng(cfg).choice(per_gpu, 256, replace=False))
+    ref = oracle.solve(b.select(idx), n_threads=os.cpu_count() or 8)
+    assert np.array_equal(sol.iters[idx], ref["iters"]), f"config {cfg}: iteration counters differ"
+    assert np.array_equal(sol.status[idx], ref["status"])
+    for k in ("F", "X", "P", "L", "viol"):
+        a, r = getattr(sol, k)[idx], ref[k]
+        same = (a == r) | (np.isnan(a) & np.isnan(r))
+        assert same.all(), f"config {cfg}: {k} differs in {np.count_nonzero(~same)} entries"
+
+
+@pytest.mark.parametrize("n", [64, 88])
+def test_long_horizons_up_to_the_shared_memory_limit(oracle, n):
+    """analysis/solve_times_test.py:60-66 sweeps gait_horizon up to 20 periods (trot: n = 200).  One CTA per instance
+    holds every iterate, matrix entry and row record of the instance in the shared memory of one SM, which ends at
+    n = 88 (218 KB); longer horizons are refused loudly (what a two-CTA cluster would take)."""
+    _require_gpu()
+    from bunmpc_b200.motions import GAITS, ROBOTS
+    from bunmpc_b200.plan_builder import build_batch
+    from bunmpc_b200.problem import SolverParams
+    from bunmpc_b200.solver import BatchSolver
+    rb, gp = ROBOTS["solo12"], GAITS["solo12"]["trot"]
+    B = 3
+    rng = np.random.default_rng(n)
+    com = np.array([0.0, 0.0, gp.nom_ht]) + rng.normal(0.0, 0.02, (B, 3))
+    foot = np.broadcast_to(rb.foot_pos, (B, 4, 3)).copy()
+    foot[:, :, :2] += rng.normal(0.0, 0.02, (B, 4, 2))
+    v_des = np.zeros((B, 3)); v_des[:, 0] = rng.uniform(0.0, 0.3, B)
+    b = build_batch(rb, gp, com, rng.normal(0.0, 0.1, (B, 3)), rng.normal(0.0, 0.02, (B, 3)), foot,
+                    rng.integers(0, 10, B) * gp.gait_dt, v_des, np.zeros(B), horizon=n)
+    assert b.n_col == n
+    prm = SolverParams(max_outer=8)
+    sol = BatchSolver(n, 4, max_batch=B).solve(b, prm)
+    ref = oracle.solve(b, oracle.default_params(max_outer=8), n_threads=B)
+    assert_same(sol, ref, f"n={n}")
+    with pytest.raises(RuntimeError, match="shared memory"):
+        BatchSolver(89, 4, max_batch=1)
