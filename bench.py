@@ -230,12 +230,23 @@ def other_workloads(device, arith, world=1, rank=0):
     st = EpisodeState(com, vcom, amom, np.array(foot), t0s.astype(np.float64), np.zeros(B))
     roll = LockstepRollouts(rb, gp, plant=TrackingPlant(0.002, 0.02, 0.0, seed=1), device=device)
     roll.run(st, v_des, 0.0, n_ticks=1)
+    roll.h2d_bytes = 0
     t0 = time.perf_counter()
     rec = roll.run(st, v_des, 0.0, n_ticks=6)
     dt = time.perf_counter() - t0
     out["lockstep_rollouts_B1024_6_ticks (host plan builder + plant in the loop, e2e)"] = {
         "solves_per_s": int((np.array([(r > 0).any(1).sum() for r in rec.iters])).sum()) / dt, "ms": 1e3 * dt,
-        "failed": int((rec.failed_at >= 0).sum())}
+        "failed": int((rec.failed_at >= 0).sum()), "h2d_bytes": int(roll.h2d_bytes)}
+    # the same loop on the device path: states up, build_problem_kernel + solve where the problem lies, plan down
+    rold = LockstepRollouts(rb, gp, plant=TrackingPlant(0.002, 0.02, 0.0, seed=1), device=device, builder="device")
+    rold.run(st, v_des, 0.0, n_ticks=1)
+    rold.h2d_bytes = 0
+    t0 = time.perf_counter()
+    rec = rold.run(st, v_des, 0.0, n_ticks=6)
+    dt = time.perf_counter() - t0
+    out["lockstep_rollouts_B1024_6_ticks_device_builder (states up, plan down, plant in the loop, e2e)"] = {
+        "solves_per_s": int((np.array([(r > 0).any(1).sum() for r in rec.iters])).sum()) / dt, "ms": 1e3 * dt,
+        "failed": int((rec.failed_at >= 0).sum()), "h2d_bytes": int(rold.h2d_bytes)}
     return out
 
 

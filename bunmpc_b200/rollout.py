@@ -96,12 +96,45 @@ class LockstepRollouts:
 
     def __init__(self, robot: RobotConstants, params: BiconvexMotionParams, plan_freq: float = 0.05,
                  plant: Optional[Callable] = None, device: int = 0, horizon: Optional[int] = None,
-                 solve_fn: Optional[Callable[[CentroidalBatch], BatchSolution]] = None):
+                 solve_fn: Optional[Callable[[CentroidalBatch], BatchSolution]] = None, builder: str = "host"):
+        """builder = "host": contact plans and references are built with numpy (plan_builder.build_batch) and the whole
+        problem crosses PCIe every tick (4.3 KB per episode); builder = "device": only the centroidal states go up
+        (230 B per episode), the problem is built by build_problem_kernel and solved where it lies
+        (BatchSolver.build_device + solve_resident); what comes back is what the plant / controller consumes (the
+        plan X, F, the step sizes and counters, and -- for TrackingPlant -- the contact plan it steps along)."""
+        if builder not in ("host", "device"):
+            raise ValueError("builder must be 'host' or 'device'")
+        if builder == "device" and solve_fn is not None:
+            raise ValueError("an injected solve_fn works on host batches: use builder='host'")
+        if builder == "device" and horizon is not None and horizon != params.horizon():
+            raise ValueError("the device builder plans over the gait's own horizon")
         self.robot, self.params, self.plan_freq, self.device = robot, params, plan_freq, device
         self.plant = plant if plant is not None else TrackingPlant()
         self.horizon = horizon if horizon is not None else params.horizon()
         self._solve_fn = solve_fn                 # tests inject the oracle here; default: the GPU solver
+        self.builder = builder
         self.launches = 0
+        self.h2d_bytes = 0                        # bytes that crossed PCIe towards the GPU (problem data or states)
+
+    def _tick_device(self, st: "EpisodeState", v_des, w_des, amom_des, L0):
+        """One replanning tick on the device path: states up, build + solve on the GPU, plan down."""
+        solver = get_solver(self.horizon, 4, st.com.shape[0], self.device)
+        dev = solver.build_device(self.robot, self.params, st.com, st.vcom, st.amom, st.foot_pos, st.t, v_des, w_des,
+                                  yaw=st.yaw, amom_des=amom_des, L0=L0)
+        o = solver.solve_resident(dev)
+        self.launches += 1
+        B, n, e = dev.B, self.horizon, 4
+        self.h2d_bytes += B * 8 * (9 + 3 * e + 1 + 3 + 1 + 2 + (3 if amom_des is not None else 0) + (2 if L0 is not None else 0))
+        host = {k: v.cpu().numpy() for k, v in o.items()}
+        sol = BatchSolution(X=host["X"], F=host["F"], P=host["P"], L=host["L"], iters=host["iters"], viol=host["viol"],
+                            status=host["status"], m=np.array([self.robot.mass]))
+        f = dev.fields
+        shared = lambda k: f[k].cpu().numpy()
+        batch = CentroidalBatch(n, e, m=shared("m").reshape(-1), rho=shared("rho").reshape(-1), x_init=shared("x_init"),
+                                cnt_plan=shared("cnt_plan").reshape(-1, n, e, 4), dt=shared("dt"), W_X=shared("W_X"),
+                                W_X_ter=shared("W_X_ter"), X_nom=shared("X_nom"), X_ter=shared("X_ter"),
+                                W_F=shared("W_F"), bounds=shared("bounds").reshape(-1, n, 6), L0=shared("L0"))
+        return batch, sol
 
     def _solve(self, batch: CentroidalBatch) -> BatchSolution:
         self.launches += 1
@@ -122,11 +155,15 @@ class LockstepRollouts:
             if idx.size == 0:
                 break
             st = state.select(idx)
-            batch = build_batch(self.robot, self.params, st.com, st.vcom, st.amom, st.foot_pos, st.t, v_des[idx],
-                                w_des[idx], yaw=st.yaw, horizon=self.horizon,
-                                amom_des=(amom_des if amom_des is None or np.ndim(amom_des) < 2 else np.asarray(amom_des)[idx]),
-                                L0=None if L is None else L[idx])
-            sol = self._solve(batch)
+            ad = amom_des if amom_des is None or np.ndim(amom_des) < 2 else np.asarray(amom_des)[idx]
+            if self.builder == "device":
+                batch, sol = self._tick_device(st, v_des[idx], w_des[idx], ad, None if L is None else L[idx])
+            else:
+                batch = build_batch(self.robot, self.params, st.com, st.vcom, st.amom, st.foot_pos, st.t, v_des[idx],
+                                    w_des[idx], yaw=st.yaw, horizon=self.horizon, amom_des=ad,
+                                    L0=None if L is None else L[idx])
+                self.h2d_bytes += batch.input_bytes()
+                sol = self._solve(batch)
             if L is None:
                 L = np.tile(sol.L[:1] * 0.0, (B, 1))
             L[idx] = sol.L                                                   # step sizes persist across replans (Q3)
@@ -167,6 +204,18 @@ class GoalPosterior:
         flat = rng.choice(p.size, size=n_goals, p=p.ravel() / p.sum())
         i, j, k = np.unravel_index(flat, p.shape)
         return np.stack([self.axes[0][i], self.axes[1][j], self.axes[2][k]], axis=1)
+
+    def sample_device(self, n_goals: int, generator=None):
+        """Goals drawn from the posterior without leaving the GPU (torch.multinomial on the flattened grid): a
+        [n_goals, 3] float64 tensor on the posterior's device.  (sample() copies the 100^3 grid to the host on every
+        call; its numpy stream is what the CPU tests pin.)"""
+        if self.device is None:
+            raise ValueError("sample_device needs a posterior created with device=...")
+        t = self._t
+        flat = t.multinomial(self.p.reshape(-1), n_goals, replacement=True, generator=generator)
+        n1, n2 = self.p.shape[1], self.p.shape[2]
+        i, j, k = flat // (n1 * n2), (flat // n2) % n1, flat % n2
+        return t.stack([self._ax[0][i], self._ax[1][j], self._ax[2][k]], dim=1)
 
     def log_likelihood(self, goals: np.ndarray, weights: Optional[np.ndarray] = None):
         """Sum over the observed goals of the log of the separable Gaussian likelihood on the grid."""

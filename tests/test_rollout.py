@@ -118,3 +118,27 @@ def test_lockstep_rollouts_gpu_equals_oracle(oracle):
     w = np.exp(-rec.tracking_error(v_des))
     d.update_batch(v_des, w); h.update_batch(v_des, w)
     assert np.allclose(d.p.cpu().numpy(), h.p, rtol=1e-9, atol=1e-300)
+
+
+@pytest.mark.gpu
+def test_lockstep_rollouts_device_builder_equals_host_builder():
+    """f-3 on the device path: states up, build_problem_kernel + solve where the problem lies, plan down.  Same records,
+    bit for bit, as the host-builder loop (disturbances included), with ~20x fewer bytes towards the GPU."""
+    import torch
+    assert torch.cuda.is_available()
+    from bunmpc_b200.rollout import GoalPosterior, LockstepRollouts, TrackingPlant
+    rb, gp, st, v_des = _initial_states(40, seed=11)
+    host = LockstepRollouts(rb, gp, plant=TrackingPlant(0.003, 0.02, 0.0, seed=4))
+    devr = LockstepRollouts(rb, gp, plant=TrackingPlant(0.003, 0.02, 0.0, seed=4), builder="device")
+    rh = host.run(st, v_des, 0.0, n_ticks=5)
+    rd = devr.run(st, v_des, 0.0, n_ticks=5)
+    assert devr.launches == 5
+    _records_equal(rd, rh)
+    assert devr.h2d_bytes * 10 < host.h2d_bytes
+    # goals drawn on the device come from the grid and follow the posterior
+    post = GoalPosterior(n=40, device="cuda:0")
+    post.update_batch(v_des, np.exp(-rd.tracking_error(v_des)))
+    g = post.sample_device(4000, generator=torch.Generator(device="cuda:0").manual_seed(1))
+    assert g.shape == (4000, 3) and g.is_cuda
+    mean_vx = float((post.p.sum((1, 2)) * post._ax[0]).sum())
+    assert abs(float(g[:, 0].mean()) - mean_vx) < 0.01
