@@ -42,8 +42,8 @@ while time.time() < t_end:
     b = synthetic.perturbed(B, robot, gait, seed=bseed, horizon_scale=scale,
                             vy_range=(-0.1, 0.1), w_range=(-0.1, 0.1),
                             weight_scale_range=(0.5, 2.0) if rng.random() < 0.3 else None)
-    if rng.random() < 0.35:                                   # any horizon 1..77 (generic kernels of every thread class)
-        n = int(rng.integers(1, 78))
+    if rng.random() < 0.35:                                   # any horizon 1..88 (every CTA size)
+        n = int(rng.integers(1, 89))
         B = min(B, 150)
         b = b.select(np.arange(B))
         b = truncate_or_tile(b, n)
