@@ -229,11 +229,12 @@ def test_per_gpu_shard_sizes_sampled(oracle, cfg, per_gpu):
         assert same.all(), f"config {cfg}: {k} differs in {np.count_nonzero(~same)} entries"
 
 
-@pytest.mark.parametrize("n", [64, 88])
-def test_long_horizons_up_to_the_shared_memory_limit(oracle, n):
-    """analysis/solve_times_test.py:60-66 sweeps gait_horizon up to 20 periods (trot: n = 200).  One CTA per instance
-    holds every iterate, matrix entry and row record of the instance in the shared memory of one SM, which ends at
-    n = 88 (218 KB); longer horizons are refused loudly (what a two-CTA cluster would take)."""
+@pytest.mark.parametrize("n", [64, 88, 89, 120, 200])
+def test_horizons_of_the_reference_timing_sweep(oracle, n):
+    """analysis/solve_times_test.py:60-66 sweeps gait_horizon up to 20 periods (trot: n = 200) and 32 (bound: n = 192).
+    Up to n = 88 an instance runs the pipelined loops; from n = 89 (CTAs of 512 threads and more) the shared memory of one
+    SM only holds the sequential loops' buffers (kernels.cuh: big_cta), up to n = 208; beyond that the solver refuses
+    loudly."""
     _require_gpu()
     from bunmpc_b200.motions import GAITS, ROBOTS
     from bunmpc_b200.plan_builder import build_batch
@@ -254,4 +255,6 @@ def test_long_horizons_up_to_the_shared_memory_limit(oracle, n):
     ref = oracle.solve(b, oracle.default_params(max_outer=8), n_threads=B)
     assert_same(sol, ref, f"n={n}")
     with pytest.raises(RuntimeError, match="shared memory"):
-        BatchSolver(89, 4, max_batch=1)
+        BatchSolver(216, 4, max_batch=1)
+    with pytest.raises(RuntimeError, match="too large"):
+        BatchSolver(249, 4, max_batch=1)
