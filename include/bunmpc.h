@@ -38,7 +38,7 @@ enum { BUNMPC_CONVERGED = 0, BUNMPC_MAX_ITERS = 1, BUNMPC_NAN = 2 };
  * path, a tolerance mode (1e-3 relative on forces and CoM/momentum), bit-exact against its own oracle twin. */
 enum { BUNMPC_ARITH_STRICT = 0, BUNMPC_ARITH_FMA = 1, BUNMPC_ARITH_MIXED = 2 };
 
-typedef struct bunmpc_solver bunmpc_solver;   /* opaque: device, stream, tables, staging buffers */
+typedef struct bunmpc_solver bunmpc_solver;   /* opaque: device, stream, staging buffers, work queue */
 
 /* Solver constants.  Defaults = the reference's member initialisers, none of which python can change
  * (biconvex.hpp:148-160, fista.hpp:52-60; num_iters is the argument of BiConvexMP::optimize). */
@@ -110,7 +110,7 @@ const char *bunmpc_last_error(void);
 void        bunmpc_default_params(bunmpc_params *p);
 
 /* BiConvexMP::BiConvexMP(m, n_col, n_eff) (biconvex.cpp:6-25): allocates everything a batch of up to
- * max_batch instances needs on `device` (tables, staging buffers, a stream).  No allocation afterwards. */
+ * max_batch instances needs on `device` (staging buffers, the time-slicing scratch, a stream).  No allocation afterwards. */
 int  bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max_batch);
 void bunmpc_destroy(bunmpc_solver *s);
 

@@ -31,8 +31,8 @@ def _batch(n, B=5, seed=0, gait="trot"):
 
 @pytest.mark.parametrize("n", [1, 2, 3, 7, 21, 33, 41, 77])
 def test_horizons_from_one_knot_to_the_largest(oracle, n):
-    """n = 1..33 run the split-role generic kernels of every thread class, 41 is the first combined-role horizon,
-    77 the largest one CTA holds (1024 threads)."""
+    """Horizons that fall into every CTA size up to 384 threads (64, 96, 128, 160, 192, 256, 384); longer ones:
+    tests/test_gpu_parity.py::test_horizons_of_the_reference_timing_sweep."""
     from bunmpc_b200.solver import BatchSolver
     from bunmpc_b200.problem import SolverParams
     b = _batch(n, B=4, seed=n)
@@ -133,7 +133,7 @@ def test_step_size_overflows_to_infinity(oracle):
 
 
 def test_randomised_soak_short():
-    """Ten seconds of profiles/soak_parity.py: random gaits, robots, horizons 1..77, batch sizes, iteration caps,
+    """Ten seconds of profiles/soak_parity.py: random gaits, robots, horizons 1..88, batch sizes, iteration caps,
     tolerances, beta/mu, initial step sizes, warm starts, arithmetic modes, slice lengths -- all bit-identical."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
