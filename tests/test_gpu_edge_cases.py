@@ -29,7 +29,7 @@ def _batch(n, B=5, seed=0, gait="trot"):
                        rng.integers(0, 10, B) * gp.gait_dt, v_des, np.zeros(B), horizon=n)
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 7, 21, 33, 41, 77])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 12, 16, 21, 28, 33, 41, 77])
 def test_horizons_from_one_knot_to_the_largest(oracle, n):
     """Horizons that fall into every CTA size up to 384 threads (64, 96, 128, 160, 192, 256, 384); longer ones:
     tests/test_gpu_parity.py::test_horizons_of_the_reference_timing_sweep."""

@@ -258,3 +258,29 @@ def test_horizons_of_the_reference_timing_sweep(oracle, n):
         BatchSolver(216, 4, max_batch=1)
     with pytest.raises(RuntimeError, match="too large"):
         BatchSolver(249, 4, max_batch=1)
+
+
+def test_three_warp_ctas_sharing_an_sm(oracle):
+    """n = 16: CTAs of three warps (two workers + the service warp), two resident per SM, which start at different
+    schedulers -- the case in which logical_warp() permutes the warp roles by scheduler placement.  400 instances keep
+    every SM's two slots busy; results must not depend on which hardware warp took which share."""
+    _require_gpu()
+    from bunmpc_b200.motions import GAITS, ROBOTS
+    from bunmpc_b200.plan_builder import build_batch
+    from bunmpc_b200.problem import SolverParams
+    from bunmpc_b200.solver import BatchSolver
+    rb, gp = ROBOTS["solo12"], GAITS["solo12"]["trot"]
+    B, n = 400, 16
+    rng = np.random.default_rng(16)
+    com = np.array([0.0, 0.0, gp.nom_ht]) + rng.normal(0.0, 0.02, (B, 3))
+    foot = np.broadcast_to(rb.foot_pos, (B, 4, 3)).copy()
+    foot[:, :, :2] += rng.normal(0.0, 0.02, (B, 4, 2))
+    v_des = np.zeros((B, 3)); v_des[:, 0] = rng.uniform(0.0, 0.3, B)
+    b = build_batch(rb, gp, com, rng.normal(0.0, 0.1, (B, 3)), rng.normal(0.0, 0.02, (B, 3)), foot,
+                    rng.integers(0, 10, B) * gp.gait_dt, v_des, np.zeros(B), horizon=n)
+    prm = SolverParams(max_outer=10)
+    s = BatchSolver(n, 4, max_batch=B)
+    assert s.kernel_info()["threads"] == 96
+    sol = s.solve(b, prm)
+    ref = oracle.solve(b, oracle.default_params(max_outer=10), n_threads=os.cpu_count() or 8)
+    assert_same(sol, ref, "n=16, two CTAs of three warps per SM")
