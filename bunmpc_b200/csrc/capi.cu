@@ -105,8 +105,11 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
     if (!out || n_col < 1 || max_batch < 1) return fail(BUNMPC_ERR_ARG, "bunmpc_create: bad argument");
     if (n_eff != 4) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: kernels are built for n_eff == 4");
     const int n = n_col, e = n_eff, nx = 9 * (n + 1), nf = 3 * e * n;
-    const int nthreads = solve_threads(n, e);             // e*n force threads / 3(n+1) state threads, one CTA per instance
+    int nthreads = solve_threads(n, e);                   // e*n force threads / 3(n+1) state threads, one CTA per instance
     if (nthreads == 0) return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: n_col too large for one CTA per instance");
+    // a horizon whose pipelined layout does not fit into the shared memory of one SM runs in the lean layout of the big
+    // CTAs (kernels.cuh: big_cta)
+    if (nthreads < 512 && smem_bytes_for(n, e, 150, nthreads) > (size_t)kMaxSmemBytes) nthreads = 512;
     if (smem_bytes_for(n, e, 150, nthreads) > (size_t)kMaxSmemBytes)
         return fail(BUNMPC_ERR_UNSUPPORTED, "bunmpc_create: n_col too large for the shared memory of one SM");
     CK(cudaSetDevice(device));

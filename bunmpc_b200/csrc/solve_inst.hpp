@@ -23,12 +23,17 @@ inline solve_fn solve_inst_x128(int arith, int ctas)
     return arith == 2 ? solve_inst_x128_2(ctas) : (arith ? solve_inst_x128_1(ctas) : solve_inst_x128_0(ctas));
 }
 
-// smallest CTA size that holds a horizon: e*n force threads and 3(n+1) state/row threads in the worker warps, plus the
-// service warp
+// CTA size for a horizon: e*n force threads and 3(n+1) state/row threads in whole worker warps, plus one more warp --
+// the service warp of short horizons (constraint rows, kernels.cuh), or at longer horizons a warp that has nothing to do
+// but the line-search decisions -- unless that warp would cost residency or registers (128 -> 160 threads: one CTA per SM
+// instead of two; 256 -> 288: 168 registers instead of 255; ...)
 inline int solve_threads(int n, int e)
 {
     const int work = (e * n > 3 * (n + 1)) ? e * n : 3 * (n + 1);
-    const int need = 32 * ((work + 31) / 32) + 32;
+    const bool service = 3 * (n + 1) <= 64;
+    const int w32 = 32 * ((work + 31) / 32);
+    auto cls = [](int nt) { return nt <= 128 ? 0 : nt <= 256 ? 1 : nt <= 384 ? 2 : nt <= 512 ? 3 : nt <= 768 ? 4 : 5; };
+    const int need = (service || cls(w32 + 32) == cls(w32)) ? w32 + 32 : w32;
 #define BUNMPC_PICK_NT(NT, MAXREG) if (need <= NT) return NT;
     BUNMPC_NT_LIST(BUNMPC_PICK_NT)
 #undef BUNMPC_PICK_NT
