@@ -30,7 +30,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 struct bunmpc_solver {
     int device = 0, n = 0, e = 0, nx = 0, nf = 0, max_batch = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
-    unsigned int *work_counter = nullptr;   // [3]: next item, finished instances, queue tail
+    unsigned int *work_counter = nullptr;   // [2 + 2 kParkQueues]: next fresh instance, finished instances, tail / head of each queue of parked instances
     int *queue = nullptr; double *sl_d = nullptr; int *sl_i = nullptr; long long *sl_c = nullptr;   // time slicing
     double *coef = nullptr;          // device, [coef_len]
     int coef_len = 0;
@@ -54,7 +54,7 @@ static size_t smem_bytes_for(int n, int e, int max_inner, int nthreads)
     return (size_t)make_layout(n, e, max_inner, nthreads / 32).total * sizeof(double);
 }
 
-static const int kMaxSmemBytes = 227 * 1024 - 64;   // dynamic + the kernel's 16 static bytes must fit the 227 KB opt-in limit
+static const int kMaxSmemBytes = 227 * 1024 - 256;  // dynamic + the kernel's static shared memory (~100 bytes) must fit the 227 KB opt-in limit
 
 static void free_solver(bunmpc_solver *s)
 {
@@ -136,8 +136,8 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
         CKS(cudaMemcpy(s->coef, c.data(), sizeof(double) * kMaxInnerTable, cudaMemcpyHostToDevice));
         s->coef_len = kMaxInnerTable;
     }
-    CKS(cudaMalloc(&s->work_counter, 3 * sizeof(unsigned int)));
-    CKS(cudaMalloc(&s->queue, sizeof(int) * kQueuePerInstance * (size_t)max_batch));
+    CKS(cudaMalloc(&s->work_counter, (2 + 2 * kParkQueues) * sizeof(unsigned int)));
+    CKS(cudaMalloc(&s->queue, sizeof(int) * kParkQueues * kQueuePerInstance * (size_t)max_batch));
     CKS(cudaMalloc(&s->sl_d, sizeof(double) * (size_t)max_batch * (2 * (size_t)nx + nf + 2)));
     CKS(cudaMalloc(&s->sl_i, sizeof(int) * 8 * (size_t)max_batch));
     CKS(cudaMalloc(&s->sl_c, sizeof(long long) * (size_t)max_batch));
@@ -284,8 +284,10 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     }
     a.slice_outer = slice; a.queue_cap = kQueuePerInstance * a.B;
     a.queue = s->queue; a.sl_d = s->sl_d; a.sl_i = s->sl_i; a.sl_c = s->sl_c;
-    CK(cudaMemsetAsync(s->work_counter, 0, 3 * sizeof(unsigned int), st));
-    if (slice > 0) CK(cudaMemsetAsync(s->queue, 0xff, sizeof(int) * (size_t)a.queue_cap, st));
+    a.long_inner = 2500.f;      // scheduling heuristic (kernels.cuh, parking code); never changes a result
+    if (const char *ev = getenv("BUNMPC_LONG_INNER")) a.long_inner = (float)atof(ev);
+    CK(cudaMemsetAsync(s->work_counter, 0, (2 + 2 * kParkQueues) * sizeof(unsigned int), st));
+    if (slice > 0) CK(cudaMemsetAsync(s->queue, 0xff, sizeof(int) * kParkQueues * (size_t)a.queue_cap, st));
     fn<<<(unsigned)grid, s->nthreads, smem, st>>>(a);
     s->launches++;
     CK(cudaGetLastError());
