@@ -148,6 +148,26 @@ def test_slice_length_never_changes_results(oracle, slice_outer):
     assert np.isfinite(sol.viol_hist[np.arange(300), sol.iters[:, 0] - 1]).all()
 
 
+@pytest.mark.parametrize("long_inner", ["0", "40", "700", "1e30"])
+def test_parked_queue_thresholds_never_change_results(oracle, monkeypatch, long_inner):
+    """Parked instances wait in four queues by predicted remaining work (longest first, kernels.cuh parking code).  The
+    threshold only decides who runs next: everything in the last queue (0), spread over all four (40, 700: the
+    instances of this batch have 100-3000 inner iterations left when they park), everything in the first (1e30), with
+    few resident CTAs (BUNMPC_MAX_CTAS) so that every queue is drained by CTAs other than the ones that filled it."""
+    _require_gpu()
+    from bunmpc_b200 import synthetic
+    from bunmpc_b200.problem import SolverParams
+    from bunmpc_b200.solver import BatchSolver
+    monkeypatch.setenv("BUNMPC_LONG_INNER", long_inner)
+    monkeypatch.setenv("BUNMPC_MAX_CTAS", "7")
+    b = synthetic.perturbed(60, "solo12", "trot", seed=77)
+    prm = SolverParams(max_outer=30, slice_outer=2)
+    sol = BatchSolver(b.n_col, b.n_eff, max_batch=64).solve(b, prm)
+    ref = oracle.solve(b, oracle.default_params(max_outer=30), n_threads=16)
+    assert sol.iters[:, 0].max() > 6                        # parked at least three times
+    assert_same(sol, ref, f"long_inner={long_inner}")
+
+
 def test_baseline_config1_full_batch_bit_for_bit(oracle):
     """BASELINE config[1] at its full size: 1024 perturbed Solo12 trot states on one B200, every instance compared
     with the oracle -- values, step sizes, iteration counters, status (the oracle needs a few seconds on the host cores)."""
