@@ -170,6 +170,8 @@ def other_workloads(device, arith, world=1, rank=0):
              ("config3_solo12_jump_n60_4096", 512, lambda B: synthetic.perturbed(B, "solo12", "jump", seed=seed, horizon_scale=2.0), None),
              ("solo12_bound_n24_8192 (bound gait, its own horizon)", 1024, lambda B: synthetic.perturbed(B, "solo12", "bound", seed=seed), None),
              ("solo12_jump_n30_8192 (jump gait, its own horizon)", 1024, lambda B: synthetic.perturbed(B, "solo12", "jump", seed=seed), None),
+             ("acyclic_jump_fwd_n25_8192 (SoloAcyclicGen replans over the whole motion, 50 outer iterations)", 1024, lambda B: synthetic.acyclic_replans(B, "jump_fwd", seed=seed), SolverParams(max_outer=50)),
+             ("acyclic_rearing_n20_8192 (50 outer iterations; replans from a standing state into the rearing phase end in NaN in the reference algorithm too)", 1024, lambda B: synthetic.acyclic_replans(B, "rearing", seed=seed), SolverParams(max_outer=50)),
              ("config4_bayes_goal+weight_samples_65536", 8192, lambda B: synthetic.config(4, B=B, seed=seed), None),
              ("solo12_trot_65536 (saturated)", 8192, lambda B: synthetic.config(1, B=B, seed=seed), None)]
     for name, per_gpu, make, prm in cases:

@@ -11,9 +11,11 @@ from .gait_planner import GaitPlanner, QuadrupedGait                            
 from .biconvex import BiconvexMP, BiConvexMP, CentroidalDynamics                        # noqa: F401
 from .solver import BatchSolver, get_solver, solve_batch                                # noqa: F401
 from .gait_gen import AbstractGaitGen, CyclicQuadrupedGaitGen, SoloMpcGaitGen            # noqa: F401
+from .acyclic import ACYCLIC_MOTIONS, ACyclicMotionParams, SoloAcyclicGen                   # noqa: F401
 from ._lib import ARITH_FMA, ARITH_MIXED, ARITH_STRICT, BunmpcError                                  # noqa: F401
 
 __all__ = ["BiconvexMP", "BiConvexMP", "CentroidalDynamics", "BatchSolver", "solve_batch", "get_solver",
            "CentroidalBatch", "BatchSolution", "SolverParams", "GaitPlanner", "QuadrupedGait",
-           "CyclicQuadrupedGaitGen", "SoloMpcGaitGen", "AbstractGaitGen",
+           "CyclicQuadrupedGaitGen", "SoloMpcGaitGen", "AbstractGaitGen", "SoloAcyclicGen", "ACyclicMotionParams",
+           "ACYCLIC_MOTIONS",
            "ARITH_STRICT", "ARITH_FMA", "ARITH_MIXED", "BunmpcError"]

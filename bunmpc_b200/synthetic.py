@@ -65,3 +65,15 @@ def config(idx: int, B=None, seed=0) -> CentroidalBatch:
         return perturbed(65536 if B is None else B, "solo12", "trot", seed=seed, vx_range=(0.0, 0.3),
                          vy_range=(-0.1, 0.1), w_range=(-0.1, 0.1), weight_scale_range=(0.5, 2.0))
     raise ValueError(idx)
+
+
+def acyclic_replans(B, motion="jump_fwd", seed=0, sigma_com=0.02, sigma_vcom=0.1, sigma_amom=0.02) -> CentroidalBatch:
+    """B replans of an acyclic motion (abstract_acyclic_gen.py): replanning instants on a 50 ms grid over the whole
+    motion, the state perturbed around the motion's first nominal state.  Solve with max_outer = ACYCLIC_MAX_OUTER."""
+    from .acyclic import ACYCLIC_MOTIONS, build_batch
+    prm = ACYCLIC_MOTIONS[motion]
+    rng = np.random.default_rng(seed)
+    x0 = np.asarray(prm.X_nom[0][0:9]) + np.concatenate([rng.normal(0, sigma_com, (B, 3)), rng.normal(0, sigma_vcom, (B, 3)),
+                                                         rng.normal(0, sigma_amom, (B, 3))], axis=1)
+    t = np.round(rng.uniform(0, prm.cnt_plan[-1][0][5], B) / 0.05) * 0.05
+    return build_batch(prm, x0, t, 0.0)

@@ -3,6 +3,7 @@
 import numpy as np
 
 from . import rpy  # noqa: F401
+from . import utils  # noqa: F401
 
 
 class Quaternion:
@@ -89,6 +90,7 @@ class FakeModel:
     def __init__(self, frame_names, nv):
         self._ids = {name: i for i, name in enumerate(frame_names)}
         self.nv = nv
+        self.nq = nv + 1
 
     def getFrameId(self, name):
         return self._ids[name]
