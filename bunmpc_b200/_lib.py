@@ -48,7 +48,8 @@ class Gait(C.Structure):
                 ("stance_percent", C.c_double * 4), ("phase_offset", C.c_double * 4),
                 ("hip_offsets", (C.c_double * 2) * 4), ("foot_size", C.c_double), ("nom_ht", C.c_double),
                 ("ori_correction", C.c_double * 3), ("I_zz", C.c_double), ("W_X", C.c_double * 9),
-                ("W_X_ter", C.c_double * 9), ("W_F", C.c_double * 12), ("rho", C.c_double)]
+                ("W_X_ter", C.c_double * 9), ("W_F", C.c_double * 12), ("rho", C.c_double),
+                ("swing_rule", C.c_int), ("reserved_", C.c_int)]
 
 
 STATE_FIELDS = ("com", "vcom", "amom", "foot_pos", "t", "v_des", "w_des", "cs_yaw", "hip_xy", "amom_des", "scales")

@@ -331,6 +331,7 @@ int bunmpc_build_problem_device(bunmpc_solver *s, const bunmpc_gait *g, const bu
     a.x_init = x_init; a.cnt_plan = cnt_plan; a.dt = dt; a.X_nom = X_nom; a.X_ter = X_ter;
     a.W_X = W_X; a.W_X_ter = W_X_ter; a.W_F = W_F; a.rho = rho;
     static_assert(sizeof(GaitDev) == sizeof(bunmpc_gait), "bunmpc_gait layout");
+    if (g->swing_rule != 0 && g->swing_rule != 1) return fail(BUNMPC_ERR_ARG, "build_problem: swing_rule must be 0 or 1");
     memcpy(&a.g, g, sizeof(GaitDev));
     build_problem_kernel<<<(a.B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     s->launches++;

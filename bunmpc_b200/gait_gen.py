@@ -12,12 +12,14 @@ from __future__ import annotations
 import numpy as np
 
 from .motions import SOLO12, BiconvexMotionParams, RobotConstants
-from .plan_builder import build_batch
+from .plan_builder import SWING_RULE_ABSTRACT, SWING_RULE_SOLO_MPC, build_batch
 from .problem import BatchSolution
 from .solver import get_solver
 
 
 class CyclicQuadrupedGaitGen:
+    swing_rule = SWING_RULE_SOLO_MPC       # the one contact-plan rule in which the reference's two cyclic generators differ
+
     def __init__(self, robot=None, r_urdf=None, x_reg=None, planning_time=0.05, q0=None, height_map=None,
                  robot_constants: RobotConstants = SOLO12, device: int = 0):
         self.robot, self.r_urdf, self.x_reg, self.q0 = robot, r_urdf, x_reg, q0
@@ -48,7 +50,7 @@ class CyclicQuadrupedGaitGen:
     # ---- the hot path, from centroidal states ----
     def _solve(self, com, vcom, amom, foot_pos, t, v_des, w_des, yaw, amom_des):
         batch = build_batch(self.rc, self.params, com, vcom, amom, foot_pos, t, v_des, w_des, yaw=yaw,
-                            amom_des=amom_des, horizon=self.horizon, L0=self.L)
+                            amom_des=amom_des, horizon=self.horizon, L0=self.L, swing_rule=self.swing_rule)
         sol = get_solver(batch.n_col, batch.n_eff, batch.B, self.device).solve(batch)
         self.L = sol.L.copy()                                    # the FISTA objects keep their L_ across replans
         self.last = (batch, sol)
@@ -109,4 +111,12 @@ class CyclicQuadrupedGaitGen:
 
 # the names the reference and upstream BiConMP use for this class
 SoloMpcGaitGen = CyclicQuadrupedGaitGen
-AbstractGaitGen = CyclicQuadrupedGaitGen
+
+
+class AbstractGaitGen(CyclicQuadrupedGaitGen):
+    """examples/mpc/abstract_cyclic_gen1.py: the robot-agnostic variant (end-effector and hip names are constructor
+    arguments, hip offsets = round(foot - com, 3) without the +-0.04 y shift -- pass them in `robot_constants`).  Its
+    contact plan leaves the Raibert step out of the second half of a swing (:211-215); costs, bounds, horizon, dt rule and
+    interpolation are those of SoloMpcGaitGen (tests/golden/plan_cases.npz holds its outputs next to SoloMpcGaitGen's).
+    `update_gait_params` has no `horizon` override there (:97)."""
+    swing_rule = SWING_RULE_ABSTRACT

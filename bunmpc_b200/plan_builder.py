@@ -16,6 +16,12 @@ from .problem import CentroidalBatch, L0_F, L0_X
 
 GRAVITY = 9.81   # abstract_cyclic_gen.py:49
 
+# The reference has two cyclic generators that differ in ONE rule of the contact plan (found by running both through
+# oracle/pinshim on the same inputs): where a foot is planned to be in the second half of its swing.
+SWING_RULE_SOLO_MPC = 0      # SoloMpcGaitGen, abstract_cyclic_gen.py:351-355: hip + yaw step + Raibert step
+SWING_RULE_ABSTRACT = 1      # AbstractGaitGen, abstract_cyclic_gen1.py:211-215: hip + yaw step (the Raibert step it
+                             # computes there is not added)
+
 
 def _b(a, B, tail):
     a = np.asarray(a, dtype=np.float64)
@@ -36,7 +42,7 @@ def rotated_hip_offsets(robot: RobotConstants, yaw):
 
 
 def build_contact_plan(robot: RobotConstants, params: BiconvexMotionParams, com, foot_pos, t, v_des, w_des,
-                       yaw=0.0, horizon=None, hip_xy=None):
+                       yaw=0.0, horizon=None, hip_xy=None, swing_rule=SWING_RULE_SOLO_MPC):
     """create_cnt_plan, abstract_cyclic_gen.py:159-414 (height_map=None, noise_std=None, mcts=None).
 
     com [B,3], foot_pos [B,e,3] (current end-effector positions; rounded to 3 dp as :211/:240 unless they
@@ -84,8 +90,8 @@ def build_contact_plan(robot: RobotConstants, params: BiconvexMotionParams, com,
                 - 0.05 * (vtrack - v_des[:, 0:2])                      # :282
             per_ph = np.round(gp.get_percent_in_phase(ft, j), 3)       # :346
             touchdown_xy = raibert + hip_loc + ang_step                # :289
-            swing_xy = np.where((per_ph < 0.5)[:, None], hip_loc + ang_step,
-                                hip_loc + ang_step + raibert)          # :351-355
+            swing_xy = np.where((per_ph < 0.5)[:, None] | (swing_rule == SWING_RULE_ABSTRACT), hip_loc + ang_step,
+                                hip_loc + ang_step + raibert)          # :351-355; abstract_cyclic_gen1.py:211-215
             xy = np.where(stance[:, None],
                           np.where(prev_stance[:, None], cnt_plan[:, i - 1, j, 1:3], touchdown_xy), swing_xy)
             z = np.where(stance & prev_stance, cnt_plan[:, i - 1, j, 3], robot.foot_size)   # :271,337,374
@@ -137,7 +143,7 @@ def build_costs(robot: RobotConstants, params: BiconvexMotionParams, x_init, dt,
 
 def build_batch(robot: RobotConstants, params: BiconvexMotionParams, com, vcom, amom, foot_pos, t, v_des, w_des,
                 yaw=0.0, amom_des=None, horizon=None, L0=None, scale_W_X=None, scale_W_F=None,
-                scale_rho=None, hip_xy=None) -> CentroidalBatch:
+                scale_rho=None, hip_xy=None, swing_rule=SWING_RULE_SOLO_MPC) -> CentroidalBatch:
     """One CentroidalBatch from centroidal states: contact plan + costs + bounds.  The optional per-instance
     scalings multiply W_X / W_X_ter, W_F and rho (BASELINE config 5's cost-weight samples)."""
     com = np.atleast_2d(np.asarray(com, dtype=np.float64))
@@ -145,7 +151,7 @@ def build_batch(robot: RobotConstants, params: BiconvexMotionParams, com, vcom, 
     x_init = np.concatenate([com, _b(vcom, B, (3,)), _b(amom, B, (3,))], axis=1)
     v_des = _b(v_des, B, (3,))
     cnt_plan, dt = build_contact_plan(robot, params, com, foot_pos, t, v_des, w_des, yaw=yaw, horizon=horizon,
-                                      hip_xy=hip_xy)
+                                      hip_xy=hip_xy, swing_rule=swing_rule)
     W_X, W_X_ter, X_nom, X_ter, W_F, bounds = build_costs(robot, params, x_init, dt, v_des, w_des, amom_des)
     rho = np.array([params.rho], dtype=np.float64)
     if scale_W_X is not None:

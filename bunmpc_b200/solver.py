@@ -204,10 +204,11 @@ class BatchSolver:
         return DeviceBatch(B=B, fields=fields, out=out, widths=w)
 
     def build_device(self, robot, params, com, vcom, amom, foot_pos, t, v_des, w_des, yaw=0.0, amom_des=None,
-                     scales=None, L0=None, hip_xy=None) -> DeviceBatch:
+                     scales=None, L0=None, hip_xy=None, swing_rule=0) -> DeviceBatch:
         """Batched problem builder ON THE DEVICE: contact plan (create_cnt_plan,
         abstract_cyclic_gen.py:159-414) and nominal/terminal references (create_costs, :564-614) from centroidal
-        states; only the states cross PCIe.  Same results, bit for bit, as plan_builder.build_batch (numpy)."""
+        states; only the states cross PCIe.  Same results, bit for bit, as plan_builder.build_batch (numpy).
+        swing_rule: plan_builder.SWING_RULE_* (which of the reference's two cyclic generators)."""
         import torch
         from .problem import L0_F, L0_X
         dev = torch.device("cuda", self.device)
@@ -236,6 +237,7 @@ class BatchSolver:
             g.phase_offset[j] = params.phase_offset[j]
             g.hip_offsets[j][0], g.hip_offsets[j][1] = robot.hip_offsets[j][0], robot.hip_offsets[j][1]
         g.foot_size, g.nom_ht, g.I_zz, g.rho = robot.foot_size, params.nom_ht, robot.I_zz, params.rho
+        g.swing_rule = int(swing_rule)
         for k in range(3):
             g.ori_correction[k] = params.ori_correction[k]
         for k in range(9):

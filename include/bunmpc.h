@@ -153,6 +153,11 @@ typedef struct {
     double ori_correction[3];
     double I_zz;                                  /* composite yaw inertia, used when w_des != 0 (:604) */
     double W_X[9], W_X_ter[9], W_F[12], rho;      /* used only when per-instance scalings are given */
+    int    swing_rule;                            /* planned location of a foot in the second half of its swing:
+                                                     0 = hip + yaw step + Raibert step (SoloMpcGaitGen,
+                                                     abstract_cyclic_gen.py:351-355), 1 = hip + yaw step only
+                                                     (AbstractGaitGen, abstract_cyclic_gen1.py:211-215) */
+    int    reserved_;
 } bunmpc_gait;
 
 typedef struct {

@@ -129,6 +129,25 @@ class FakeRobot:
             d.Ycrb[1] = _Inertia(I_composite)
 
 
+# ---- AbstractGaitGen (examples/mpc/abstract_cyclic_gen1.py:28-29) builds its own model from the urdf path: the harness
+# registers the FakeRobot that "is" that urdf beforehand ----
+_URDF_ROBOTS = {}
+
+
+def register_urdf(path, robot):
+    _URDF_ROBOTS[path] = robot
+
+
+def JointModelFreeFlyer():
+    return None
+
+
+def buildModelFromUrdf(path, root_joint=None):
+    robot = _URDF_ROBOTS[path]
+    robot.model.createData = lambda: robot.data
+    return robot.model
+
+
 def forwardKinematics(model, data, q, v=None):
     pass
 

@@ -9,7 +9,11 @@ Run in the build container:   make -C oracle/refshim && python tests/golden/make
 
 Stored per case: what bunmpc_b200.plan_builder / the CUDA build_problem_kernel take as inputs (centroidal state, foot
 positions, time in the gait, desired velocities, yaw, orientation-correction momentum, hip offsets, yaw inertia) and
-what the reference handed to its solver (cnt_plan, dt, X_nom, X_ter, W_X, W_X_ter, W_F, bounds, rho)."""
+what the reference handed to its solver (cnt_plan, dt, X_nom, X_ter, W_X, W_X_ter, W_F, bounds, rho).
+
+Every case is also run through the reference's OTHER cyclic generator, `AbstractGaitGen` of
+examples/mpc/abstract_cyclic_gen1.py (create_cnt_plan :136-237, create_costs :239-322), on the same state, with the hip
+offsets that class derives itself (round(foot - com, 3) at q0) and its own default horizon: keys `<case>/gen1/...`."""
 import importlib
 import os
 import sys
@@ -34,7 +38,8 @@ def quat_rpy(r, p, y):
 def main():
     sys.path[:0] = [os.path.join(ROOT, "oracle", "pinshim"), os.path.join(REF, "mpc"), REF, ROOT]
     import pinocchio as pin                                     # the stand-in
-    gen = importlib.import_module("abstract_cyclic_gen")       # the reference's own file
+    gen = importlib.import_module("abstract_cyclic_gen")       # the reference's own files
+    gen1 = importlib.import_module("abstract_cyclic_gen1")
     motions = {g: getattr(importlib.import_module(f"motions.cyclic.solo12_{g}"), g) for g in ("trot", "bound", "jump")}
     rng = np.random.default_rng(0)
     out, names = {}, []
@@ -47,7 +52,8 @@ def main():
         q0 = np.zeros(19); q0[2] = 0.25; q0[6] = 1.0
         com0 = np.array([0.0, 0.0, 0.2]) + rng.normal(0, 0.003, 3)
         I_comp = np.diag([0.03, 0.06, 0.0885]) + rng.normal(0, 1e-3, (3, 3))
-        robot.inject(com=com0, hip_pos=hip0 + np.array([0, 0, 0.2]) + rng.normal(0, 1e-3, (4, 3)), I_composite=I_comp)
+        hip_pos0 = hip0 + np.array([0, 0, 0.2]) + rng.normal(0, 1e-3, (4, 3))
+        robot.inject(com=com0, hip_pos=hip_pos0, I_composite=I_comp)
         gg = gen.SoloMpcGaitGen(robot, "solo12.urdf", np.zeros(37), 0.05, q0)
         # time in the gait: on the planning grid, on phase edges, off the grid, several periods ahead
         t = float([0.0, 0.05, 0.3, 0.15, 0.25, 0.1, 0.013, 0.262, 1.2, 0.5, 0.45, 2.05][ci % 12])
@@ -88,6 +94,22 @@ def main():
         out[f"{name}/gait"] = gait
         for k, v_ in vals.items():
             out[f"{name}/{k}"] = np.asarray(v_, dtype=np.float64)
+        # ---- the same state through AbstractGaitGen (abstract_cyclic_gen1.py); no further random draws ----
+        robot1 = pin.FakeRobot(robot.model.mass, nv=18)
+        robot1.inject(com=com0, hip_pos=hip_pos0, foot_pos=hip0 * [1, 1, 0] + [0, 0, 0.018], I_composite=I_comp)
+        pin.register_urdf("solo12.urdf", robot1)
+        g1 = gen1.AbstractGaitGen("solo12.urdf", list(pin.FakeRobot.FRAMES[0:4]), list(pin.FakeRobot.FRAMES[4:8]),
+                                  np.zeros(37), 0.05, q0)
+        g1.update_gait_params(prm, t)
+        robot1.inject(com=com, foot_pos=feet, hg=hg)
+        g1.create_cnt_plan(q, v, t, v_des, w_des)
+        g1.create_costs(q, v, v_des, w_des, ori_des)
+        mp1 = g1.mp
+        vals1 = dict(hip_offsets=g1.offsets.copy(), hip_xy=np.array([np.matmul(R_yaw, g1.offsets[j])[0:2] for j in range(4)]),
+                     horizon=g1.horizon, cnt_plan=np.array(mp1.cnt_plan), dt=np.array(mp1.dt), X_nom=mp1.X_nom, X_ter=mp1.X_ter,
+                     W_X=mp1.W_X, W_X_ter=mp1.W_X_ter, W_F=mp1.W_F, bounds=mp1.bounds, rho=mp1.rho, x_init=g1.X_init.copy())
+        for k, v_ in vals1.items():
+            out[f"{name}/gen1/{k}"] = np.asarray(v_, dtype=np.float64)
         # the reference's own gait record, to pin bunmpc_b200/motions.py against it
         for k in ("gait_period", "gait_dt", "gait_horizon", "nom_ht", "rho", "step_ht"):
             out[f"motion/{gait}/{k}"] = np.float64(getattr(prm, k))
@@ -104,6 +126,7 @@ def load(path=OUT):
     for name in z["names"]:
         d = {k: z[f"{name}/{k}"] for k in IN_KEYS + OUT_KEYS}
         d["gait"] = str(z[f"{name}/gait"])
+        d["gen1"] = {k: z[f"{name}/gen1/{k}"] for k in OUT_KEYS + ("hip_offsets", "hip_xy", "horizon")}
         cases.append((str(name), d))
     motions = {}
     for key in z.files:

@@ -83,3 +83,63 @@ def test_device_builder_equals_reference_python():
 def motions_horizon(gait):
     from bunmpc_b200 import motions
     return motions.GAITS["solo12"][gait].horizon()
+
+
+# ---- the reference's other cyclic generator: AbstractGaitGen, examples/mpc/abstract_cyclic_gen1.py ----
+def _gen1_robot(d):
+    from bunmpc_b200 import motions
+    g1 = d["gen1"]
+    return dataclasses.replace(motions.SOLO12, mass=float(d["mass"]), hip_offsets=g1["hip_offsets"], I_zz=float(d["I_zz"]))
+
+
+@pytest.mark.parametrize("name,d", CASES, ids=[c[0] for c in CASES])
+def test_host_builder_equals_abstract_gait_gen(name, d):
+    """Same states through abstract_cyclic_gen1.py: its own hip offsets (round(foot - com, 3)), its swing rule (no Raibert
+    step in the second half of a swing, :211-215); costs and bounds are those of SoloMpcGaitGen."""
+    from bunmpc_b200 import motions, plan_builder
+    g1 = d["gen1"]
+    prm = motions.GAITS["solo12"][d["gait"]]
+    n = int(g1["horizon"])
+    b = plan_builder.build_batch(_gen1_robot(d), prm, d["com"][None], d["vcom"][None], d["amom"][None], d["foot_pos"][None],
+                                 d["t"][None], d["v_des"][None], d["w_des"][None], yaw=d["yaw"][None],
+                                 amom_des=d["amom_des"][None], hip_xy=g1["hip_xy"][None],
+                                 swing_rule=plan_builder.SWING_RULE_ABSTRACT)
+    assert b.n_col == n
+    for k in ("cnt_plan", "dt", "x_init", "X_nom", "X_ter"):
+        assert np.array_equal(getattr(b, k)[0], g1[k]), k
+    assert np.array_equal(np.broadcast_to(b.W_X, (1, 9 * n))[0], g1["W_X"])
+    assert np.array_equal(np.broadcast_to(b.W_F, (1, 12 * n))[0], g1["W_F"])
+    assert np.array_equal(np.broadcast_to(b.bounds, (1, n, 6))[0], g1["bounds"])
+    # the rule matters: with SoloMpcGaitGen's rule the plan differs whenever a foot is late in its swing inside the horizon
+    b0 = plan_builder.build_batch(_gen1_robot(d), prm, d["com"][None], d["vcom"][None], d["amom"][None], d["foot_pos"][None],
+                                  d["t"][None], d["v_des"][None], d["w_des"][None], yaw=d["yaw"][None],
+                                  amom_des=d["amom_des"][None], hip_xy=g1["hip_xy"][None])
+    assert not np.array_equal(b0.cnt_plan[0], g1["cnt_plan"])
+
+
+def test_abstract_gait_gen_class_uses_its_rule():
+    from bunmpc_b200 import AbstractGaitGen, SoloMpcGaitGen, plan_builder
+    assert AbstractGaitGen.swing_rule == plan_builder.SWING_RULE_ABSTRACT
+    assert SoloMpcGaitGen.swing_rule == plan_builder.SWING_RULE_SOLO_MPC
+    assert issubclass(AbstractGaitGen, SoloMpcGaitGen)
+
+
+@pytest.mark.gpu
+def test_device_builder_equals_abstract_gait_gen():
+    """build_problem_kernel with bunmpc_gait.swing_rule = 1 == abstract_cyclic_gen1.py, bit for bit."""
+    from bunmpc_b200 import motions, plan_builder
+    from bunmpc_b200.solver import BatchSolver
+    solvers = {}
+    for name, d in CASES:
+        g1 = d["gen1"]
+        prm = motions.GAITS["solo12"][d["gait"]]
+        n = int(g1["horizon"])
+        s = solvers.setdefault(n, BatchSolver(n, 4, max_batch=1))
+        dev = s.build_device(_gen1_robot(d), prm, d["com"][None], d["vcom"][None], d["amom"][None], d["foot_pos"][None],
+                             d["t"][None], d["v_des"][None], d["w_des"][None], yaw=d["yaw"][None],
+                             amom_des=d["amom_des"][None], hip_xy=g1["hip_xy"][None],
+                             swing_rule=plan_builder.SWING_RULE_ABSTRACT)
+        f = {k: v.cpu().numpy() for k, v in dev.fields.items() if v is not None}
+        assert np.array_equal(f["cnt_plan"][0], g1["cnt_plan"].reshape(-1)), (name, "cnt_plan")
+        for k in ("dt", "x_init", "X_nom", "X_ter"):
+            assert np.array_equal(f[k][0], g1[k]), (name, k)
