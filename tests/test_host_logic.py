@@ -116,7 +116,7 @@ def test_gait_gen_shim_sizes_and_interpolation():
     """update_gait_params sizes (abstract_cyclic_gen.py:125-153) and the 1 kHz interpolation (:677-692)."""
     import bunmpc_b200 as pkg
     from bunmpc_b200.motions import solo12_trot
-    assert pkg.SoloMpcGaitGen is pkg.CyclicQuadrupedGaitGen is pkg.AbstractGaitGen
+    assert pkg.SoloMpcGaitGen is pkg.CyclicQuadrupedGaitGen and issubclass(pkg.AbstractGaitGen, pkg.CyclicQuadrupedGaitGen)
     gg = pkg.CyclicQuadrupedGaitGen(None, None, None, planning_time=0.05)
     gg.update_gait_params(solo12_trot, 0.0)
     assert gg.horizon == 20 and gg.ik_horizon == 10 and gg.size == 3      # min(10, int(0.05/0.05)+2) = 3
