@@ -55,6 +55,11 @@ class Gait(C.Structure):
 STATE_FIELDS = ("com", "vcom", "amom", "foot_pos", "t", "v_des", "w_des", "cs_yaw", "hip_xy", "amom_des", "scales")
 
 
+class AcyclicMotion(C.Structure):
+    _fields_ = [("n_cnt", C.c_int), ("n_nom", C.c_int), ("n_box", C.c_int), ("dt_arr", C.c_void_p), ("cnt_plan", C.c_void_p),
+                ("X_nom", C.c_void_p), ("bounds", C.c_void_p), ("X_ter", C.c_void_p), ("t0", C.c_double)]
+
+
 class States(C.Structure):
     _fields_ = [("batch", C.c_int)] + [(f, In) for f in STATE_FIELDS]
 
@@ -67,7 +72,7 @@ class Solution(C.Structure):
 # every symbol include/bunmpc.h declares
 EXPORTS = ("bunmpc_version", "bunmpc_last_error", "bunmpc_default_params", "bunmpc_create", "bunmpc_destroy",
            "bunmpc_launch_count", "bunmpc_kernel_info", "bunmpc_expand_device", "bunmpc_solve_expanded_device",
-           "bunmpc_solve_compact_device", "bunmpc_build_problem_device", "bunmpc_solve_compact_host", "bunmpc_solve_expanded_host",
+           "bunmpc_solve_compact_device", "bunmpc_build_problem_device", "bunmpc_build_acyclic_device", "bunmpc_solve_compact_host", "bunmpc_solve_expanded_host",
            "bunmpc_goal_stats_device", "bunmpc_centroidal_mats_host", "bunmpc_measure_fp64_peak", "bunmpc_selftest_division", "bunmpc_host_alloc", "bunmpc_host_free")
 
 _lib = None
@@ -101,6 +106,7 @@ def lib():
     L.bunmpc_solve_compact_device.argtypes = [C.c_void_p, C.POINTER(CompactProblem), C.POINTER(Params),
                                               C.POINTER(Solution), C.c_void_p]
     L.bunmpc_build_problem_device.argtypes = [C.c_void_p, C.POINTER(Gait), C.POINTER(States)] + [C.c_void_p] * 10
+    L.bunmpc_build_acyclic_device.argtypes = [C.c_void_p, C.POINTER(AcyclicMotion), C.c_int, C.POINTER(In), C.POINTER(In)] + [C.c_void_p] * 6
     L.bunmpc_solve_compact_host.argtypes = [C.c_void_p, C.POINTER(CompactProblem), C.POINTER(Params),
                                             C.POINTER(Solution)]
     L.bunmpc_solve_expanded_host.argtypes = [C.c_void_p, C.POINTER(ExpandedProblem), C.POINTER(Params),

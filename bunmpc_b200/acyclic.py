@@ -241,11 +241,22 @@ class SoloAcyclicGen:
             self.size += 1
         self.L = None                                               # a new KinoDynMP (fresh FISTA objects) is made here, :56
 
-    def optimize_centroidal_batch(self, x_init, t, params: SolverParams = None) -> BatchSolution:
-        """B replans in one launch; 50 outer iterations (:319) unless params says otherwise."""
+    def optimize_centroidal_batch(self, x_init, t, params: SolverParams = None, builder: str = "host") -> BatchSolution:
+        """B replans in one launch; 50 outer iterations (:319) unless params says otherwise.  builder = "device": only
+        the states and replanning instants go up, build_acyclic_kernel looks the knots up where the problem is solved."""
         from .solver import get_solver
-        batch = build_batch(self.params, x_init, t, self.t0, L0=self.L)
         prm = params if params is not None else SolverParams(max_outer=ACYCLIC_MAX_OUTER)
+        if builder == "device":
+            x_init = np.atleast_2d(np.asarray(x_init, dtype=np.float64))
+            s = get_solver(int(self.params.n_col), self.n_eff, x_init.shape[0], self.device)
+            dev = s.build_acyclic_device(self.params, x_init, t, self.t0, L0=self.L)
+            o = s.solve_resident(dev, params=prm)
+            sol = BatchSolution(X=o["X"].cpu().numpy(), F=o["F"].cpu().numpy(), P=o["P"].cpu().numpy(), L=o["L"].cpu().numpy(),
+                                iters=o["iters"].cpu().numpy(), viol=o["viol"].cpu().numpy(), status=o["status"].cpu().numpy(),
+                                m=np.array([self.params.mass]), cycles=o["cycles"].cpu().numpy())
+            self.last = (dev, sol)
+            return sol
+        batch = build_batch(self.params, x_init, t, self.t0, L0=self.L)
         sol = get_solver(batch.n_col, batch.n_eff, batch.B, self.device).solve(batch, prm)
         self.last = (batch, sol)
         return sol

@@ -339,6 +339,28 @@ int bunmpc_build_problem_device(bunmpc_solver *s, const bunmpc_gait *g, const bu
     return BUNMPC_OK;
 }
 
+int bunmpc_build_acyclic_device(bunmpc_solver *s, const bunmpc_acyclic_motion *m, int batch, const bunmpc_in *x_init,
+                                const bunmpc_in *t, double *cnt_plan, double *dt, double *X_nom, double *X_ter,
+                                double *bounds, void *stream)
+{
+    if (!s || !m || !x_init || !t || !x_init->ptr || !t->ptr || !cnt_plan || !dt || !X_nom || !X_ter || !bounds)
+        return fail(BUNMPC_ERR_ARG, "build_acyclic: null argument");
+    if (!m->dt_arr || !m->cnt_plan || !m->X_nom || !m->bounds || !m->X_ter || m->n_cnt < 1 || m->n_nom < 1 || m->n_box < 1)
+        return fail(BUNMPC_ERR_ARG, "build_acyclic: incomplete motion tables");
+    if (batch < 1) return fail(BUNMPC_ERR_ARG, "build_acyclic: batch < 1");
+    if (s->e != 4) return fail(BUNMPC_ERR_UNSUPPORTED, "build_acyclic: four end effectors");
+    CK(cudaSetDevice(s->device));
+    AcyclicArgs a;
+    a.B = batch; a.n = s->n; a.n_cnt = m->n_cnt; a.n_nom = m->n_nom; a.n_box = m->n_box;
+    a.dt_arr = m->dt_arr; a.cnt = m->cnt_plan; a.nom = m->X_nom; a.box = m->bounds; a.X_ter_rec = m->X_ter; a.t0 = m->t0;
+    a.x_init = mk(*x_init); a.t = mk(*t);
+    a.cnt_plan = cnt_plan; a.dt = dt; a.X_nom = X_nom; a.X_ter = X_ter; a.bounds = bounds;
+    build_acyclic_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    s->launches++;
+    CK(cudaGetLastError());
+    return BUNMPC_OK;
+}
+
 int bunmpc_goal_stats_device(bunmpc_solver *s, int batch, const bunmpc_in *goals, const bunmpc_in *errors, double *out17,
                              void *stream)
 {

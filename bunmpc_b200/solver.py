@@ -278,6 +278,56 @@ class BatchSolver:
         self._keep = st_t      # keep the state tensors alive until the (asynchronous) kernel has consumed them
         return DeviceBatch(B=B, fields=fields, out=res, widths=self._widths())
 
+    def build_acyclic_device(self, motion, x_init, t, t0=0.0, L0=None) -> DeviceBatch:
+        """The acyclic generator's problem builder ON THE DEVICE (SoloAcyclicGen.create_contact_plan / create_costs,
+        abstract_acyclic_gen.py:74-190) for B replans: only x_init [B,9] and the replanning instants t [B] cross PCIe,
+        the motion's time tables are uploaded once per (solver, motion).  Same results, bit for bit, as
+        acyclic.build_batch (numpy)."""
+        import torch
+        from .problem import L0_F, L0_X
+        dev = torch.device("cuda", self.device)
+        x_init = np.atleast_2d(np.asarray(x_init, dtype=np.float64))
+        B, n, e = x_init.shape[0], self.n_col, self.n_eff
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch}")
+        if int(motion.n_col) != n:
+            raise ValueError("the motion's number of knots does not match the solver")
+        f64 = dict(dtype=torch.float64, device=dev)
+        one = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(1, -1))).to(dev)
+        cache = self.__dict__.setdefault("_acyclic_tables", {})
+        tab = cache.get(id(motion))
+        if tab is None:
+            tab = dict(dt_arr=one(motion.dt_arr), cnt=one(motion.cnt_plan), nom=one(motion.X_nom), box=one(motion.bounds),
+                       X_ter=one(motion.X_ter), rho=one([motion.rho]), m=one([motion.mass]), W_X=one(np.tile(motion.W_X, n)),
+                       W_X_ter=one(motion.W_X_ter), W_F=one(np.tile(motion.W_F, n)), motion=motion)
+            cache[id(motion)] = tab
+        xs = torch.from_numpy(np.ascontiguousarray(x_init)).to(dev)
+        ts = torch.from_numpy(np.array(np.broadcast_to(np.asarray(t, dtype=np.float64), (B,)), order="C", copy=True)).to(dev)
+        m = _lib.AcyclicMotion()
+        m.n_cnt, m.n_nom, m.n_box = len(motion.cnt_plan), len(motion.X_nom), len(motion.bounds)
+        m.dt_arr, m.cnt_plan, m.X_nom = tab["dt_arr"].data_ptr(), tab["cnt"].data_ptr(), tab["nom"].data_ptr()
+        m.bounds, m.X_ter, m.t0 = tab["box"].data_ptr(), tab["X_ter"].data_ptr(), float(t0)
+        out = dict(cnt_plan=torch.empty((B, n * e * 4), **f64), dt=torch.empty((B, n), **f64),
+                   X_nom=torch.empty((B, 9 * n), **f64), X_ter=torch.empty((B, 9), **f64), bounds=torch.empty((B, 6 * n), **f64))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        xin, tin = _lib.In(xs.data_ptr(), 9), _lib.In(ts.data_ptr(), 1)
+        _lib.check(_lib.lib().bunmpc_build_acyclic_device(
+            self._h, C.byref(m), B, C.byref(xin), C.byref(tin), *(C.c_void_p(out[k].data_ptr()) for k in
+                                                               ("cnt_plan", "dt", "X_nom", "X_ter", "bounds")),
+            C.c_void_p(stream)), "bunmpc_build_acyclic_device")
+        fields = dict(out)
+        fields.update(x_init=xs, m=tab["m"], rho=tab["rho"], W_X=tab["W_X"], W_X_ter=tab["W_X_ter"], W_F=tab["W_F"],
+                      L0=one([L0_F, L0_X]) if L0 is None else torch.from_numpy(np.array(
+                          np.broadcast_to(np.asarray(L0, dtype=np.float64), (B, 2)), order="C", copy=True)).to(dev),
+                      X0=None, F0=None, P0=None)
+        res = dict(X=torch.empty((B, self.nx), **f64), F=torch.empty((B, self.nf), **f64),
+                   P=torch.empty((B, self.nx), **f64), L=torch.empty((B, 2), **f64),
+                   iters=torch.empty((B, 5), dtype=torch.int32, device=dev), viol=torch.empty((B,), **f64),
+                   status=torch.empty((B,), dtype=torch.int32, device=dev),
+                   cycles=torch.empty((B,), dtype=torch.int64, device=dev))
+        self._keep = (xs, ts)
+        return DeviceBatch(B=B, fields=fields, out=res, widths=self._widths())
+
     def solve_resident(self, dev: DeviceBatch, params: Optional[SolverParams] = None,
                        arith: int = _lib.ARITH_STRICT):
         """Expand + solve on device-resident inputs, asynchronous on torch's current stream."""

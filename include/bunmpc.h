@@ -182,6 +182,25 @@ int bunmpc_build_problem_device(bunmpc_solver *s, const bunmpc_gait *g, const bu
                                 double *cnt_plan, double *dt, double *X_nom, double *X_ter, double *W_X,
                                 double *W_X_ter, double *W_F, double *rho, void *stream);
 
+/* ---- the same for the ACYCLIC generator (SoloAcyclicGen, examples/mpc/abstract_acyclic_gen.py:74-190): a motion is
+ * three time tables (examples/motions/weight_abstract.py:46-83), every knot of a replan at time t is looked up in them.
+ * All pointers are DEVICE pointers; the tables are uploaded once per motion. */
+typedef struct {
+    int n_cnt, n_nom, n_box;      /* segments per table (each >= 1) */
+    const double *dt_arr;         /* [n_col] */
+    const double *cnt_plan;       /* [n_cnt][4][6]  c, x, y, z, t_start, t_end per foot */
+    const double *X_nom;          /* [n_nom][11]    9 values, t_start, t_end */
+    const double *bounds;         /* [n_box][8]     6 values, t_start, t_end */
+    const double *X_ter;          /* [9] */
+    double t0;                    /* time the motion started (update_motion_params, :42-54) */
+} bunmpc_acyclic_motion;
+
+/* x_init [B][9] (passed through to X_nom's first knot, :183), t [B] replanning instants; writes cnt_plan [B][n][4][4],
+ * dt [B][n], X_nom [B][9n], X_ter [B][9], bounds [B][n][6].  Asynchronous on `stream`. */
+int bunmpc_build_acyclic_device(bunmpc_solver *s, const bunmpc_acyclic_motion *m, int batch, const bunmpc_in *x_init,
+                                const bunmpc_in *t, double *cnt_plan, double *dt, double *X_nom, double *X_ter,
+                                double *bounds, void *stream);
+
 /* Sufficient statistics of the Bayesian goal update over one rank's shard (the reference's grid posterior with a Gaussian
  * likelihood centred at the sampled goal, locosafedagger_modified.py:357-402): goals [B][3] (batch stride in elements,
  * e.g. the desired velocity X_ter + 3 with stride 9), errors [B] (NaN counts as 0) -> out17 = [N, sum g (3),

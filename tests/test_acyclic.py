@@ -101,3 +101,50 @@ def test_acyclic_generator_replans_carry_step_sizes():
         L = ref["L"]
         assert f_int.shape == (prm.n_col * int(prm.dt_arr[0] / 0.001), 12)
         assert np.array_equal(f_int[0], ref["F"][0, 0:12]) and np.array_equal(f_int[-1], ref["F"][0, -12:])
+
+
+@pytest.mark.gpu
+def test_device_builder_equals_reference_python():
+    """build_acyclic_kernel (bunmpc_build_acyclic_device): all golden cases of a motion and motion start in one launch ==
+    the reference's own python, bit for bit."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from bunmpc_b200.acyclic import ACYCLIC_MOTIONS
+    from bunmpc_b200.solver import BatchSolver
+    checked = 0
+    for motion in sorted(MOTIONS):
+        prm = ACYCLIC_MOTIONS[motion]
+        s = BatchSolver(prm.n_col, 4, max_batch=32)
+        for t0 in (0.0, 0.1):
+            ds = [d for _, d in CASES if d["motion"] == motion and float(d["t0"]) == t0]
+            dev = s.build_acyclic_device(prm, np.stack([d["x_init"] for d in ds]), np.array([float(d["t"]) for d in ds]), t0)
+            f = {k: v.cpu().numpy() for k, v in dev.fields.items() if v is not None}
+            for k in ("cnt_plan", "dt", "X_nom", "X_ter", "bounds"):
+                want = np.stack([d[k].reshape(-1) for d in ds])
+                assert np.array_equal(f[k], want), (motion, t0, k)
+            checked += len(ds)
+        s.close()
+    assert checked == len(CASES)
+
+
+@pytest.mark.gpu
+def test_acyclic_device_path_equals_host_path():
+    """SoloAcyclicGen.optimize_centroidal_batch(builder="device") == builder="host" == oracle (rearing_jump: +-inf boxes)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from bunmpc_b200.acyclic import ACYCLIC_MAX_OUTER, ACYCLIC_MOTIONS, SoloAcyclicGen, build_batch
+    from oracle import oracle
+    b = _perturbed("rearing_jump", 40, seed=5)
+    prm = ACYCLIC_MOTIONS["rearing_jump"]
+    rng = np.random.default_rng(5)
+    t = np.round(rng.uniform(0, 1.4, 40) / 0.05) * 0.05
+    g = SoloAcyclicGen()
+    g.update_motion_params(prm, None, 0.0)
+    host = g.optimize_centroidal_batch(b.x_init, t)
+    devs = g.optimize_centroidal_batch(b.x_init, t, builder="device")
+    ref = oracle.solve(build_batch(prm, b.x_init, t, 0.0), oracle.default_params(max_outer=ACYCLIC_MAX_OUTER), n_threads=16)
+    for k in ("X", "F", "P", "L", "viol", "iters", "status"):
+        assert np.array_equal(getattr(host, k), ref[k], equal_nan=True), k
+        assert np.array_equal(getattr(devs, k), ref[k], equal_nan=True), k
