@@ -12,8 +12,8 @@ typedef void (*solve_fn)(const SolveArgs);
 // service warp (kernels.cuh).  The pipelined FISTA loops keep the Hessian rows, the constraint rows, the iterate triples
 // and the sums in flight in registers and want ~250 of them; a scheduler (16K registers) then holds two warps, an SM
 // eight: 2 CTAs of 128 threads (the trot horizon), 1 of 256.  From 384 threads on the budget shrinks
-// (168 / 128 / 80 / 64 registers) and rows move to shared-memory records or spill.
-#define BUNMPC_NT_LIST(X) X(64, 255) X(96, 255) X(128, 255) X(160, 255) X(192, 255) X(256, 255) X(384, 168) X(512, 128) X(768, 80) X(1024, 64)
+// (168 / 128 / 96 / 80 / 64 registers) and rows move to shared-memory records or spill.
+#define BUNMPC_NT_LIST(X) X(64, 255) X(96, 255) X(128, 255) X(160, 255) X(192, 255) X(256, 255) X(384, 168) X(512, 128) X(640, 96) X(768, 80) X(1024, 64)
 // occupancy variant of the 128-thread kernel (BUNMPC_CTAS=3 in the environment, see capi.cu)
 solve_fn solve_inst_x128_0(int ctas);
 solve_fn solve_inst_x128_1(int ctas);
@@ -32,7 +32,7 @@ inline int solve_threads(int n, int e)
     const int work = (e * n > 3 * (n + 1)) ? e * n : 3 * (n + 1);
     const bool service = 3 * (n + 1) <= 64;
     const int w32 = 32 * ((work + 31) / 32);
-    auto cls = [](int nt) { return nt <= 128 ? 0 : nt <= 256 ? 1 : nt <= 384 ? 2 : nt <= 512 ? 3 : nt <= 768 ? 4 : 5; };
+    auto cls = [](int nt) { return nt <= 128 ? 0 : nt <= 256 ? 1 : nt <= 384 ? 2 : nt <= 512 ? 3 : nt <= 640 ? 4 : nt <= 768 ? 5 : 6; };
     const int need = (service || cls(w32 + 32) == cls(w32)) ? w32 + 32 : w32;
 #define BUNMPC_PICK_NT(NT, MAXREG) if (need <= NT) return NT;
     BUNMPC_NT_LIST(BUNMPC_PICK_NT)

@@ -249,12 +249,13 @@ def test_per_gpu_shard_sizes_sampled(oracle, cfg, per_gpu):
         assert same.all(), f"config {cfg}: {k} differs in {np.count_nonzero(~same)} entries"
 
 
-@pytest.mark.parametrize("n", [64, 88, 89, 120, 200])
+@pytest.mark.parametrize("n", [64, 93, 94, 120, 128, 129, 150, 160, 161, 192, 200, 206])
 def test_horizons_of_the_reference_timing_sweep(oracle, n):
     """analysis/solve_times_test.py:60-66 sweeps gait_horizon up to 20 periods (trot: n = 200) and 32 (bound: n = 192).
-    Up to n = 88 an instance runs the pipelined loops; from n = 89 (CTAs of 512 threads and more) the shared memory of one
-    SM only holds the sequential loops' buffers (kernels.cuh: big_cta), up to n = 208; beyond that the solver refuses
-    loudly."""
+    Up to n = 160 an instance runs the pipelined loops -- from n = 94 on (CTAs of 512 and 640 threads) without the bank
+    padding and the row records (kernels.cuh: big_cta); beyond (768 and 1024 threads, seq_cta) the shared memory of one
+    SM only holds the sequential loops' buffers, up to n = 206; beyond that the solver refuses loudly.  The horizons
+    here sit on both sides of every CTA-size step."""
     _require_gpu()
     from bunmpc_b200.motions import GAITS, ROBOTS
     from bunmpc_b200.plan_builder import build_batch
@@ -271,11 +272,19 @@ def test_horizons_of_the_reference_timing_sweep(oracle, n):
                     rng.integers(0, 10, B) * gp.gait_dt, v_des, np.zeros(B), horizon=n)
     assert b.n_col == n
     prm = SolverParams(max_outer=8)
-    sol = BatchSolver(n, 4, max_batch=B).solve(b, prm)
+    s = BatchSolver(n, 4, max_batch=B)
+    assert s.kernel_info()["threads"] == {64: 256, 93: 384, 94: 512, 120: 512, 128: 512, 129: 640, 150: 640, 160: 640,
+                                          161: 768, 192: 768, 200: 1024, 206: 1024}[n]
+    sol = s.solve(b, prm)
     ref = oracle.solve(b, oracle.default_params(max_outer=8), n_threads=B)
     assert_same(sol, ref, f"n={n}")
+    b.L0 = np.array([[1.0, 40.0]])            # tiny step sizes: rejections, i.e. the replay with the sequential loops
+    sol = s.solve(b, prm)
+    ref = oracle.solve(b, oracle.default_params(max_outer=8), n_threads=B)
+    assert ref["iters"][:, 3:5].min() > 3
+    assert_same(sol, ref, f"n={n} with rejections")
     with pytest.raises(RuntimeError, match="shared memory"):
-        BatchSolver(216, 4, max_batch=1)
+        BatchSolver(207, 4, max_batch=1)
     with pytest.raises(RuntimeError, match="too large"):
         BatchSolver(249, 4, max_batch=1)
 
