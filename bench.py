@@ -390,6 +390,18 @@ def main():
         torch.cuda.synchronize()
         kt.append(a.elapsed_time(b) * 1e-3)
     k_time = float(np.mean(kt))
+    # the same on every rank: how unequal the shards are (a step ends with collectives, i.e. with the slowest rank), and
+    # how much work each shard holds
+    rank_info = None
+    if world > 1:
+        mine = torch.tensor([1e3 * k_time, float(iters[:, 1:3].sum())], dtype=torch.float64, device="cuda")
+        allr = torch.zeros((world, 2), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.cpu().numpy()
+        rank_info = {"solve_kernel_ms_per_rank": [round(float(v), 3) for v in allr[:, 0]],
+                     "inner_iterations_per_rank": [int(v) for v in allr[:, 1]],
+                     "note": "a step takes the slowest rank's solve plus the exchange; mean / max of the kernel times is "
+                             "the ceiling of the weak-scaling efficiency for i.i.d. shards"}
 
     # ---- e2e: host buffers in, host buffers out, every copy inside the timed region ----
     # N = 1: the reference-facing C ABI call bunmpc_solve_compact_host (pinned inputs -> H2D -> kernels -> D2H).
@@ -498,6 +510,7 @@ def main():
         # the busiest memory pipe (ncu): shared-memory data stage; wavefronts per inner iteration from the ncu capture of
         # this same workload, scaled by the live iteration counters and the live kernel time
         "roofline_smem": smem_roofline(iters, k_time, clocks, info, ncu),
+        **({"shard_balance": rank_info} if rank_info else {}),
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_ach / hbm_peak,
                          "traffic": traffic,   # same ncu capture as roofline.traffic
