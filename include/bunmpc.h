@@ -53,9 +53,9 @@ typedef struct {
     int    slice_outer; /* scheduling only, results never depend on it: outer iterations an instance runs before it is
                          * parked and re-queued (time slicing).  0 = automatic (8 when the batch exceeds the resident
                          * CTAs, else off), < 0 = off.  Parked instances are resumed longest predicted remainder first
-                         * (four queues; the estimate extrapolates the decay of the dynamics violation over the slice);
-                         * environment BUNMPC_LONG_INNER = the predicted remaining inner iterations that separate the
-                         * queues (x 1/2, x 1, x 2; default 2500) -- a tuning knob, it never changes a result */
+                         * (eight queues; the estimate extrapolates the decay of the dynamics violation over the slice);
+                         * environment BUNMPC_LONG_INNER = the scale of the predicted remaining inner iterations that
+                         * separate the queues (x 0.2 .. x 3.6; default 2500) -- a tuning knob, it never changes a result */
 } bunmpc_params;
 
 typedef struct {

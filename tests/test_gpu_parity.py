@@ -150,8 +150,8 @@ def test_slice_length_never_changes_results(oracle, slice_outer):
 
 @pytest.mark.parametrize("long_inner", ["0", "40", "700", "1e30"])
 def test_parked_queue_thresholds_never_change_results(oracle, monkeypatch, long_inner):
-    """Parked instances wait in four queues by predicted remaining work (longest first, kernels.cuh parking code).  The
-    threshold only decides who runs next: everything in the last queue (0), spread over all four (40, 700: the
+    """Parked instances wait in eight queues by predicted remaining work (longest first, kernels.cuh parking code).  The
+    threshold only decides who runs next: everything in the last queue (0), spread over all of them (40, 700: the
     instances of this batch have 100-3000 inner iterations left when they park), everything in the first (1e30), with
     few resident CTAs (BUNMPC_MAX_CTAS) so that every queue is drained by CTAs other than the ones that filled it."""
     _require_gpu()
