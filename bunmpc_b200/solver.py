@@ -295,12 +295,15 @@ class BatchSolver:
         f64 = dict(dtype=torch.float64, device=dev)
         one = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(1, -1))).to(dev)
         cache = self.__dict__.setdefault("_acyclic_tables", {})
-        tab = cache.get(id(motion))
+        arrs = [np.ascontiguousarray(np.asarray(getattr(motion, k), dtype=np.float64)) for k in
+                ("dt_arr", "cnt_plan", "X_nom", "bounds", "X_ter", "W_X", "W_X_ter", "W_F")]
+        key = hash(tuple(a.tobytes() for a in arrs) + (float(motion.rho), float(motion.mass)))   # the record may be edited
+        tab = cache.get(key)
         if tab is None:
             tab = dict(dt_arr=one(motion.dt_arr), cnt=one(motion.cnt_plan), nom=one(motion.X_nom), box=one(motion.bounds),
                        X_ter=one(motion.X_ter), rho=one([motion.rho]), m=one([motion.mass]), W_X=one(np.tile(motion.W_X, n)),
                        W_X_ter=one(motion.W_X_ter), W_F=one(np.tile(motion.W_F, n)), motion=motion)
-            cache[id(motion)] = tab
+            cache[key] = tab
         xs = torch.from_numpy(np.ascontiguousarray(x_init)).to(dev)
         ts = torch.from_numpy(np.array(np.broadcast_to(np.asarray(t, dtype=np.float64), (B,)), order="C", copy=True)).to(dev)
         m = _lib.AcyclicMotion()
