@@ -42,9 +42,9 @@ while time.time() < t_end:
     b = synthetic.perturbed(B, robot, gait, seed=bseed, horizon_scale=scale,
                             vy_range=(-0.1, 0.1), w_range=(-0.1, 0.1),
                             weight_scale_range=(0.5, 2.0) if rng.random() < 0.3 else None)
-    if rng.random() < 0.35:                                   # any horizon 1..88 (every CTA size)
-        n = int(rng.integers(1, 89))
-        B = min(B, 150)
+    if rng.random() < 0.35:                                   # any horizon 1..SOAK_NMAX (every CTA size; default 88)
+        n = int(rng.integers(1, int(os.environ.get("SOAK_NMAX", "88")) + 1))
+        B = min(B, 150 if n <= 88 else 12)
         b = b.select(np.arange(B))
         b = truncate_or_tile(b, n)
     prm = SolverParams(max_outer=int(rng.choice([3, 10, 25, 100])), max_inner=int(rng.choice([1, 2, 3, 4, 5, 9, 40, 150])),
