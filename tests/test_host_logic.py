@@ -126,3 +126,25 @@ def test_gait_gen_shim_sizes_and_interpolation():
     assert np.array_equal(out[0], knots[0]) and np.array_equal(out[29], knots[1]) and np.array_equal(out[30], knots[1])
     with pytest.raises(ImportError):
         gg.optimize(np.zeros(19), np.zeros(18), 0.0, np.array([0.2, 0, 0]), 0.0)
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference`: the CPU arm of the bench contract (the oracle on the host cores, a bounded sample of
+    the same workload) prints one JSON line with the keys the driver reads; no GPU involved."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "centroidal_mpc_solves_per_sec" and d["unit"] == "solves/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert "BASELINE config[1]" in d["config"]["workload"] and d["config"]["n_col"] == 20
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
