@@ -303,6 +303,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="instances per GPU per step")
     ap.add_argument("--arith", default="strict", choices=["strict", "fma", "mixed"])
+    ap.add_argument("--split", default="balanced", choices=["balanced", "fixed"],
+                    help="multi-GPU only: 'balanced' = one fresh-instance counter for all GPUs over NVLink peer memory "
+                         "(bunmpc_b200.dist.BalancedSolver), 'fixed' = instance i -> rank i mod G (ShardedSolver)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     args = ap.parse_args()
@@ -319,7 +322,7 @@ def main():
     import torch
     import torch.distributed as dist
     from bunmpc_b200 import synthetic, ARITH_FMA, ARITH_MIXED, ARITH_STRICT
-    from bunmpc_b200.dist import ShardedSolver
+    from bunmpc_b200.dist import BalancedSolver, ShardedSolver
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -331,16 +334,28 @@ def main():
     # ONE global batch of world * B perturbed states (the same on every rank), sharded interleaved: instance i -> rank
     # i mod world.  Weak scaling: B instances per GPU at every N.
     global_batch = synthetic.config(1, B=world * B, seed=0)
-    sharded = ShardedSolver(global_batch.n_col, global_batch.n_eff, shard_batch=B, device=local_rank)
-    dev = sharded.upload_global(global_batch)
+    balanced = None
+    if world > 1 and args.split == "balanced":
+        try:
+            balanced = BalancedSolver(global_batch.n_col, global_batch.n_eff, job_batch=world * B, device=local_rank)
+        except RuntimeError as exc:        # every rank raises or none does (the ranks agree inside the constructor)
+            if rank == 0:
+                print(f"bench: balanced split unavailable ({exc}); using the fixed split", file=sys.stderr)
+    if balanced is not None:
+        dev = balanced.upload_global(global_batch)          # the whole job on every GPU, rank-major rows
+        sharded, solver = None, balanced.solver
+    else:
+        sharded = ShardedSolver(global_batch.n_col, global_batch.n_eff, shard_batch=B, device=local_rank)
+        dev = sharded.upload_global(global_batch)
+        solver = sharded.solver
     batch = global_batch.shard(rank, world)
-    solver = sharded.solver
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def step_resident():
-        # the package's multi-GPU step: solve, fixed-order statistics kernel + all_reduce, all_gather of F and X
-        return sharded.step(arith=arith)
+        # the package's multi-GPU step.  fixed split: solve, statistics kernel + all_reduce, all_gather of F and X;
+        # balanced: zero the result rows, solve what this GPU pulls from the job counter, all_reduce of the rows, statistics
+        return balanced.step(arith=arith) if balanced is not None else sharded.step(arith=arith)
 
     def barrier():
         torch.cuda.synchronize()
@@ -377,18 +392,28 @@ def main():
     value = world * B * args.steps / t_max
 
     out = {k: v.cpu().numpy() for k, v in dev.out.items()}
+    if balanced is not None:        # the rows this GPU solved in the last step (its cycle counters are set there only)
+        took = out["cycles"] > 0
+        out = {k: v[took] for k, v in out.items()}
     iters = out["iters"]
 
     # ---- solve-kernel time alone (events around the solve launch only), for the roofline ----
     kt = []
+    kflops = []
     for _ in range(max(3, min(args.steps, 5))):
         flush.zero_()
+        if balanced is not None:
+            balanced.flat.zero_()
+            barrier()               # two solves of a job are separated by a collective (the job counters alternate)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         solver.solve_resident(dev, arith=arith)
         b.record(stream)
         torch.cuda.synchronize()
         kt.append(a.elapsed_time(b) * 1e-3)
+        if balanced is not None:    # which instances a GPU pulls differs from launch to launch: count them per launch
+            tk = dev.out["cycles"] > 0
+            kflops.append(algorithmic_flops(batch.n_col, dev.out["iters"][tk].cpu().numpy()))
     k_time = float(np.mean(kt))
     # the same on every rank: how unequal the shards are (a step ends with collectives, i.e. with the slowest rank), and
     # how much work each shard holds
@@ -417,13 +442,25 @@ def main():
         t = torch.from_numpy(np.ascontiguousarray(a.reshape(a.shape[0], -1))).pin_memory()
         pinned[f] = t
         setattr(batch, f, t.numpy().reshape(a.shape))
-    outbuf = {k: torch.empty(v.shape, dtype=torch.from_numpy(v).dtype).pin_memory() for k, v in out.items()}
+    if balanced is not None:        # every rank reads back the rows of ITS instances (all rows are on every GPU after a step)
+        outbuf = {k: torch.empty(dev.out[k][balanced.own].shape, dtype=dev.out[k].dtype).pin_memory()
+                  for k in BalancedSolver.EXCHANGED}
+    else:
+        outbuf = {k: torch.empty(v.shape, dtype=torch.from_numpy(v).dtype).pin_memory() for k, v in out.items()}
     outnp = {k: v.numpy() for k, v in outbuf.items()}
     stats_host = torch.empty(17, dtype=torch.float64).pin_memory()
 
     def e2e_step():
         if world == 1:
             solver.solve(batch, arith=arith, out=outnp)
+            return
+        if balanced is not None:    # own instances up, to the other GPUs over NVLink, step, own rows down
+            balanced.load_own_rows(pinned)
+            o = balanced.step(arith=arith)
+            for k, v in outbuf.items():
+                v.copy_(o[k][balanced.own], non_blocking=True)
+            stats_host.copy_(balanced.stats, non_blocking=True)
+            torch.cuda.synchronize()
             return
         for f, t in pinned.items():
             dev.fields[f].copy_(t, non_blocking=True)
@@ -449,6 +486,10 @@ def main():
     h2d = batch.input_bytes()
     d2h = int(sum(v.numel() * v.element_size() for v in outbuf.values())) + (17 * 8 if world > 1 else 0)
 
+    if balanced is not None:        # what follows are this rank's own solves: back to the local instance counter
+        barrier()
+        _lib.check(_lib.lib().bunmpc_set_job_counter(solver._h, None, 0), "bunmpc_set_job_counter")
+
     # ---- p50 latency of a single solve through the host API (B = 1) ----
     one = batch.select(np.arange(1))
     lat = []
@@ -469,7 +510,7 @@ def main():
 
     # ---- roofline of the solve kernel ----
     fp64_peak = solver.measure_fp64_peak()
-    flops = algorithmic_flops(batch.n_col, iters)
+    flops = float(np.mean(kflops)) if kflops else algorithmic_flops(batch.n_col, iters)
     achieved = flops / k_time * 1e-12
     peaks = {}
     try:
@@ -489,7 +530,13 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "instances_per_gpu_per_step": B, "n_col": batch.n_col, "n_eff": batch.n_eff,
                    "arith": args.arith, "l2": "flushed between steps (256 MiB write)",
-                   "sharding": f"one global batch of {world * B} instances, instance i -> rank i mod {world}" + ("; per step: NCCL all_gather of F and X, all_reduce of 17 posterior statistics (bunmpc_b200.dist.ShardedSolver)" if world > 1 else ""),
+                   "sharding": (f"one global batch of {world * B} instances resident on every GPU; the CTAs of all GPUs pull "
+                                "instance ids from ONE counter in rank 0's HBM (system-scope atomics over NVLink peer "
+                                "memory, CUDA IPC); per step: NCCL all_reduce of the zero-filled result rows (exact), "
+                                "all_reduce of 17 posterior statistics (bunmpc_b200.dist.BalancedSolver)"
+                                if balanced is not None else
+                                f"one global batch of {world * B} instances, instance i -> rank i mod {world}" + ("; per step: NCCL all_gather of F and X, all_reduce of 17 posterior statistics (bunmpc_b200.dist.ShardedSolver)" if world > 1 else "")),
+                   **({"split": "balanced" if balanced is not None else "fixed"} if world > 1 else {}),
                    "kernel": info},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

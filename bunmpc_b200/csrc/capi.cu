@@ -30,6 +30,8 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 struct bunmpc_solver {
     int device = 0, n = 0, e = 0, nx = 0, nf = 0, max_batch = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
+    unsigned int *job_counters = nullptr;   // [2] fresh-instance counters of a multi-GPU job (bunmpc_set_job_counter), device or peer memory
+    int job_owner = 0; unsigned long long job_step = 0;
     unsigned int *work_counter = nullptr;   // [2 + 2 kParkQueues]: next fresh instance, finished instances, tail / head of each queue of parked instances
     int *queue = nullptr; double *sl_d = nullptr; int *sl_i = nullptr; long long *sl_c = nullptr;   // time slicing
     double *coef = nullptr;          // device, [coef_len]
@@ -89,6 +91,52 @@ void bunmpc_default_params(bunmpc_params *p)
     p->slice_outer = 0;
 }
 
+// ---- one fresh-instance counter for all ranks of a multi-GPU job: a device allocation of the owner, exported as a CUDA
+// IPC handle, mapped by the other ranks' processes (peer memory over NVLink) ----
+int bunmpc_job_counter_create(int device, void **ptr, unsigned char handle[64])
+{
+    if (!ptr || !handle) return fail(BUNMPC_ERR_ARG, "job_counter_create: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+    CK(cudaSetDevice(device));
+    void *p = nullptr;
+    CK(cudaMalloc(&p, 256));
+    CK(cudaMemset(p, 0, 256));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(BUNMPC_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memcpy(handle, &h, 64);
+    *ptr = p;
+    return BUNMPC_OK;
+}
+
+int bunmpc_job_counter_open(int device, const unsigned char handle[64], void **ptr)
+{
+    if (!ptr || !handle) return fail(BUNMPC_ERR_ARG, "job_counter_open: null argument");
+    CK(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(BUNMPC_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    *ptr = p;
+    return BUNMPC_OK;
+}
+
+int bunmpc_job_counter_release(void *ptr, int owner)
+{
+    if (!ptr) return BUNMPC_OK;
+    cudaError_t e = owner ? cudaFree(ptr) : cudaIpcCloseMemHandle(ptr);
+    if (e != cudaSuccess) return fail(BUNMPC_ERR_CUDA, std::string("job_counter_release: ") + cudaGetErrorString(e));
+    return BUNMPC_OK;
+}
+
+int bunmpc_set_job_counter(bunmpc_solver *s, void *counters, int owner)
+{
+    if (!s) return fail(BUNMPC_ERR_ARG, "set_job_counter: null solver");
+    s->job_counters = (unsigned int *)counters; s->job_owner = owner ? 1 : 0; s->job_step = 0;
+    return BUNMPC_OK;
+}
+
 void *bunmpc_host_alloc(unsigned long long bytes)
 {
     void *p = nullptr;
@@ -136,7 +184,7 @@ int bunmpc_create(bunmpc_solver **out, int device, int n_col, int n_eff, int max
         CKS(cudaMemcpy(s->coef, c.data(), sizeof(double) * kMaxInnerTable, cudaMemcpyHostToDevice));
         s->coef_len = kMaxInnerTable;
     }
-    CKS(cudaMalloc(&s->work_counter, (2 + 2 * kParkQueues) * sizeof(unsigned int)));
+    CKS(cudaMalloc(&s->work_counter, kWorkCounters * sizeof(unsigned int)));
     CKS(cudaMalloc(&s->queue, sizeof(int) * kParkQueues * kQueuePerInstance * (size_t)max_batch));
     CKS(cudaMalloc(&s->sl_d, sizeof(double) * (size_t)max_batch * (2 * (size_t)nx + nf + 2)));
     CKS(cudaMalloc(&s->sl_i, sizeof(int) * 8 * (size_t)max_batch));
@@ -286,7 +334,16 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     a.queue = s->queue; a.sl_d = s->sl_d; a.sl_i = s->sl_i; a.sl_c = s->sl_c;
     a.long_inner = 2500.f;      // scheduling heuristic (kernels.cuh, parking code); never changes a result
     if (const char *ev = getenv("BUNMPC_LONG_INNER")) a.long_inner = (float)atof(ev);
-    CK(cudaMemsetAsync(s->work_counter, 0, (2 + 2 * kParkQueues) * sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(s->work_counter, 0, kWorkCounters * sizeof(unsigned int), st));
+    a.job_counter = nullptr;
+    if (s->job_counters) {
+        // solve k of the job pulls from counter k & 1; the owner clears the other one for solve k + 1.  Between two solves
+        // of a job every rank runs a collective (the exchange of the results), so that counter is idle now and stays idle
+        // until this rank's kernel -- which follows the memset in stream order -- has finished
+        a.job_counter = s->job_counters + (s->job_step & 1ull);
+        if (s->job_owner) CK(cudaMemsetAsync(s->job_counters + ((s->job_step + 1ull) & 1ull), 0, sizeof(unsigned int), st));
+        s->job_step++;
+    }
     if (slice > 0) CK(cudaMemsetAsync(s->queue, 0xff, sizeof(int) * kParkQueues * (size_t)a.queue_cap, st));
     fn<<<(unsigned)grid, s->nthreads, smem, st>>>(a);
     s->launches++;

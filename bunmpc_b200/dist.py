@@ -151,6 +151,149 @@ class ShardedSolver:
         return t.view(self.world, self.shard_batch, w).transpose(0, 1).reshape(self.world * self.shard_batch, w)
 
 
+class BalancedSolver:
+    """The multi-GPU step with ONE fresh-instance counter for the whole job (include/bunmpc.h, "multi-GPU jobs").
+
+    A fixed split waits for its slowest shard: the instances' costs spread 4x, so the slowest of G shards of 1024 carries
+    about 2 % more work than the average one, and how close a shard gets to its own throughput bound varies by another
+    1-2 %.  The instances are independent, so no collective can fix that -- scheduling can: every rank keeps ALL
+    instances of the job in its HBM (10.6 KB each), the CTAs of every GPU pull instance ids from a counter in the memory
+    of rank 0's GPU (system-scope atomics over NVLink; the counter is mapped into the other ranks' processes by CUDA
+    IPC), and a GPU that draws cheap instances simply draws more of them.  Each rank thus fills a SUBSET of the rows of
+    its (zeroed) result buffer; one NCCL all_reduce(sum) over the buffers viewed as int64 -- x + 0 is exact for every bit
+    pattern, NaN payloads and -0.0 included -- leaves every rank with all results, which is the exchange step
+    BASELINE.json names (the all_gather of the fixed split), followed by the same statistics reduction as ShardedSolver.
+
+    Rows are kept rank-major (row r * shard + j  <->  instance j * world + r of the global batch), so a rank's own
+    instances are a contiguous slice: `own` below.  One process per GPU; world == 1 degenerates to a plain solve."""
+
+    # result fields that every rank needs after a step, in this order at the front of the flat buffer; P (warm starts)
+    # and the cycle counters stay with the rank that solved the row
+    EXCHANGED = ("X", "F", "L", "viol", "iters", "status")
+
+    def __init__(self, n_col: int, n_eff: int = 4, job_batch: int = 8192, device: int = 0):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        from .solver import BatchSolver
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        if job_batch % (2 * self.world):
+            raise ValueError("job_batch must be a multiple of 2 * world (int32 result fields are exchanged as int64 words)")
+        self.device, self.job_batch, self.shard = device, job_batch, job_batch // self.world
+        self.solver = BatchSolver(n_col, n_eff, max_batch=job_batch, device=device)
+        self.stats = torch.zeros(17, dtype=torch.float64, device=torch.device("cuda", device))
+        self._counters = C.c_void_p()
+        self.dev = None
+        if self.world > 1:
+            L, ok, handle = _lib.lib(), 1, None
+            if self.rank == 0:
+                buf = C.create_string_buffer(64)
+                ok = int(L.bunmpc_job_counter_create(device, C.byref(self._counters), buf) == _lib.OK)
+                handle = buf.raw
+            box = [handle]
+            dist.broadcast_object_list(box, src=0)
+            if self.rank != 0:
+                ok = int(box[0] is not None and
+                         L.bunmpc_job_counter_open(device, box[0], C.byref(self._counters)) == _lib.OK)
+            flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", device))
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) != 1:
+                self.close()
+                raise RuntimeError("BalancedSolver: the job counter could not be mapped into every rank's process "
+                                   "(CUDA IPC): " + (L.bunmpc_last_error() or b"").decode())
+            _lib.check(L.bunmpc_set_job_counter(self.solver._h, self._counters, int(self.rank == 0)), "bunmpc_set_job_counter")
+
+    def close(self):
+        from . import _lib
+        if getattr(self, "_counters", None) is not None and self._counters.value:
+            if getattr(self, "solver", None) is not None and self.solver._h.value:
+                _lib.lib().bunmpc_set_job_counter(self.solver._h, None, 0)
+            _lib.lib().bunmpc_job_counter_release(self._counters, int(self.rank == 0))
+            self._counters.value = None
+        if getattr(self, "solver", None) is not None:
+            self.solver.close()
+
+    def row_order(self):
+        """row -> instance of the global batch (rank-major rows of the interleaved split)"""
+        return np.concatenate([np.arange(r, self.job_batch, self.world) for r in range(self.world)])
+
+    @property
+    def own(self):
+        return slice(self.rank * self.shard, (self.rank + 1) * self.shard)
+
+    def upload_global(self, batch: CentroidalBatch):
+        """Every rank puts the WHOLE job in its HBM (identical `batch` on every rank)."""
+        import torch
+        if batch.B != self.job_batch:
+            raise ValueError("batch size != job_batch")
+        self.dev = self.solver.upload(batch.select(self.row_order()))
+        B, dev = self.job_batch, torch.device("cuda", self.device)
+        shapes = dict(X=((B, self.solver.nx), torch.float64), F=((B, self.solver.nf), torch.float64), L=((B, 2), torch.float64),
+                      viol=((B,), torch.float64), iters=((B, 5), torch.int32), status=((B,), torch.int32),
+                      P=((B, self.solver.nx), torch.float64), cycles=((B,), torch.int64))
+        words = {k: int(np.prod(sh)) * (1 if dt != torch.int32 else 0) + (int(np.prod(sh)) // 2 if dt == torch.int32 else 0)
+                 for k, (sh, dt) in shapes.items()}
+        self.flat = torch.zeros(sum(words.values()), dtype=torch.int64, device=dev)
+        off = 0
+        for k in self.EXCHANGED + ("P", "cycles"):
+            sh, dt = shapes[k]
+            self.dev.out[k] = self.flat[off:off + words[k]].view(dt).view(sh)
+            off += words[k]
+            if k == self.EXCHANGED[-1]:
+                self.n_exchanged = off
+        return self.dev
+
+    def load_own_rows(self, pinned: dict):
+        """e2e: this rank's instances arrive from ITS host (pinned tensors of its shard, [shard, w] per per-instance
+        field), go up into its rows and reach the other ranks over NVLink (one in-place all_gather per field)."""
+        import torch.distributed as dist
+        for f, t in pinned.items():
+            g = self.dev.fields[f]
+            if g is None or g.shape[0] == 1:
+                continue
+            g[self.own].copy_(t, non_blocking=True)
+            if self.world > 1:
+                dist.all_gather_into_tensor(g, g[self.own])
+
+    def step(self, params=None, arith=0, stats=True):
+        """zero the result rows, solve what this GPU pulls, exchange; returns the dict of FULL result tensors
+        (X, F, L, viol, iters, status: all rows on every rank; P, cycles: the rows this rank solved)."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        self.flat.zero_()
+        out = self.solver.solve_resident(self.dev, params=params, arith=arith)
+        if self.world > 1:
+            dist.all_reduce(self.flat[:self.n_exchanged], op=dist.ReduceOp.SUM)
+        if stats:
+            g, e = self.dev.fields["X_ter"], out["viol"]
+            o = self.rank * self.shard
+            gin = _lib.In(g.data_ptr() + 3 * 8 + (0 if g.shape[0] == 1 else 9 * 8 * o), 0 if g.shape[0] == 1 else 9)
+            ein = _lib.In(e.data_ptr() + 8 * o, 1)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib().bunmpc_goal_stats_device(self.solver._h, int(self.shard), C.byref(gin), C.byref(ein),
+                                                           C.c_void_p(self.stats.data_ptr()), C.c_void_p(stream)),
+                       "bunmpc_goal_stats_device")
+            if self.world > 1:
+                dist.all_reduce(self.stats, op=dist.ReduceOp.SUM)
+        return out
+
+    def gathered(self, name: str, ordered: bool = True):
+        """Results of the last step on this rank, all rows; ordered=True: row i = instance i of the global batch."""
+        t = self.dev.out[name]
+        if not ordered or self.world == 1:
+            return t
+        w = t.shape[1] if t.dim() > 1 else 1
+        return t.view(self.world, self.shard, w).transpose(0, 1).reshape(self.job_batch, w)
+
+
 # ---------------------------------------------------------------------------------------------------
 # Bayesian goal update (grid posterior over velocity goals), sufficient statistics over ranks
 # ---------------------------------------------------------------------------------------------------

@@ -201,6 +201,22 @@ int bunmpc_build_acyclic_device(bunmpc_solver *s, const bunmpc_acyclic_motion *m
                                 const bunmpc_in *t, double *cnt_plan, double *dt, double *X_nom, double *X_ter,
                                 double *bounds, void *stream);
 
+/* ---- multi-GPU jobs with ONE fresh-instance counter ----------------------------------------------------------
+ * The instances of the path are independent, so what a multi-GPU job needs is balance, not a collective: every rank holds
+ * all B instances of the job in its HBM and the CTAs of all GPUs pull instance ids from one counter in the memory of one
+ * GPU (system-scope atomics over NVLink / NVSwitch peer memory) -- the GPUs then finish together whatever the
+ * instances cost, where a fixed split i -> rank i mod G waits for the slowest shard.  Parked instances (time slicing)
+ * stay on the GPU that started them.  Every rank solves a SUBSET of the rows of its output buffers and leaves the
+ * other rows untouched (zero them first; the ranks' buffers then combine by a bitwise-exact integer sum).
+ * Protocol: the owner calls bunmpc_job_counter_create and sends the 64-byte CUDA IPC handle to the other ranks'
+ * processes, which call bunmpc_job_counter_open; every rank calls bunmpc_set_job_counter on its solver; then all ranks
+ * call the same solve entry point the same number of times with batch = B, with a collective of the job (the
+ * exchange of the results) between two solves.  counters == NULL switches back to the local counter. */
+int bunmpc_job_counter_create(int device, void **counters, unsigned char ipc_handle[64]);
+int bunmpc_job_counter_open(int device, const unsigned char ipc_handle[64], void **counters);
+int bunmpc_job_counter_release(void *counters, int owner);
+int bunmpc_set_job_counter(bunmpc_solver *s, void *counters, int owner);
+
 /* Sufficient statistics of the Bayesian goal update over one rank's shard (the reference's grid posterior with a Gaussian
  * likelihood centred at the sampled goal, locosafedagger_modified.py:357-402): goals [B][3] (batch stride in elements,
  * e.g. the desired velocity X_ter + 3 with stride 9), errors [B] (NaN counts as 0) -> out17 = [N, sum g (3),
