@@ -303,9 +303,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="instances per GPU per step")
     ap.add_argument("--arith", default="strict", choices=["strict", "fma", "mixed"])
-    ap.add_argument("--split", default="balanced", choices=["balanced", "fixed"],
-                    help="multi-GPU only: 'balanced' = one fresh-instance counter for all GPUs over NVLink peer memory "
-                         "(bunmpc_b200.dist.BalancedSolver), 'fixed' = instance i -> rank i mod G (ShardedSolver)")
+    ap.add_argument("--split", default="fixed", choices=["fixed", "balanced"],
+                    help="multi-GPU only: 'fixed' = instance i -> rank i mod G (ShardedSolver, the default: measured equal or "
+                         "faster at 2 and 8 GPUs, DESIGN.md section 7), 'balanced' = one fresh-instance counter for all GPUs "
+                         "over NVLink peer memory (bunmpc_b200.dist.BalancedSolver)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     args = ap.parse_args()
