@@ -3,9 +3,12 @@
 part of it that is the hot path: contact plan + costs + centroidal solve + the 1 kHz interpolation of the plan.
 
 What is NOT here: the whole-body IK (crocoddyl DDP, `KinoDynMP.optimize` beyond `dyn.optimize`) and pinocchio
-kinematics -- both out of scope and absent from this image.  `optimize(q, v, ...)` therefore
-needs pinocchio to turn (q, v) into the centroidal state and raises a clear error without it; the entry points that
-start from the centroidal state (`optimize_centroidal`, `optimize_centroidal_batch`) are complete and run on the GPU.
+kinematics -- both out of scope and absent from this image.  `optimize(q, v, ...)` uses the caller's
+pinocchio robot wrapper to turn (q, v) into the centroidal problem exactly as the reference does (`centroidal_inputs`;
+pinned bit for bit against the reference's own python with the injected-kinematics wrapper of oracle/pinshim,
+tests/test_plan_golden.py), solves it on the GPU and returns (None, None, f_int): xs / us are the IK's.  Without
+pinocchio it raises a clear error; the entry points that start from the centroidal state (`optimize_centroidal`,
+`optimize_centroidal_batch`) need nothing but numpy and the GPU.
 """
 from __future__ import annotations
 
@@ -48,9 +51,10 @@ class CyclicQuadrupedGaitGen:
         self.L = None                                            # a new KinoDynMP is created here in the reference (:133)
 
     # ---- the hot path, from centroidal states ----
-    def _solve(self, com, vcom, amom, foot_pos, t, v_des, w_des, yaw, amom_des):
+    def _solve(self, com, vcom, amom, foot_pos, t, v_des, w_des, yaw, amom_des, hip_xy=None):
         batch = build_batch(self.rc, self.params, com, vcom, amom, foot_pos, t, v_des, w_des, yaw=yaw,
-                            amom_des=amom_des, horizon=self.horizon, L0=self.L, swing_rule=self.swing_rule)
+                            amom_des=amom_des, horizon=self.horizon, L0=self.L, hip_xy=hip_xy,
+                            swing_rule=self.swing_rule)
         sol = get_solver(batch.n_col, batch.n_eff, batch.B, self.device).solve(batch)
         self.L = sol.L.copy()                                    # the FISTA objects keep their L_ across replans
         self.last = (batch, sol)
@@ -63,11 +67,12 @@ class CyclicQuadrupedGaitGen:
         segs = [np.linspace(knots[i], knots[i + 1], int(dt[i] / 0.001)) for i in range(size)]
         return np.vstack(segs)
 
-    def optimize_centroidal(self, com, vcom, amom, foot_pos, t, v_des, w_des, yaw=0.0, amom_des=None):
+    def optimize_centroidal(self, com, vcom, amom, foot_pos, t, v_des, w_des, yaw=0.0, amom_des=None, hip_xy=None):
         """One replan from the centroidal state.  Returns (com_int, mom_int, f_int) at 1 kHz like :677-692, plus the
-        raw solution in self.last.  f_int rows are the 3*n_eff stacked contact forces."""
+        raw solution in self.last.  f_int rows are the 3*n_eff stacked contact forces.  hip_xy [n_eff, 2]: the yaw-rotated
+        hip offsets if the caller has them (optimize(q, v, ...) passes the reference's own product)."""
         batch, sol = self._solve(np.atleast_2d(com), vcom, amom, np.asarray(foot_pos)[None], t, np.asarray(v_des)[None],
-                                 w_des, yaw, amom_des)
+                                 w_des, yaw, amom_des, None if hip_xy is None else np.asarray(hip_xy)[None])
         n, e = batch.n_col, batch.n_eff
         dt = batch.dt[0]
         F = sol.F[0].reshape(n, 3 * e)
@@ -81,30 +86,47 @@ class CyclicQuadrupedGaitGen:
         _, sol = self._solve(com, vcom, amom, foot_pos, t, v_des, w_des, yaw, amom_des)
         return sol
 
-    def optimize(self, q, v, t, v_des, w_des, X_wm=None, F_wm=None, P_wm=None, noise_std=None, mcts_x_y_cnt_loc=None,
-                 v_feet_des=None, ee_pos=None, z_height=None):
-        """abstract_cyclic_gen.py:629-698.  Needs pinocchio (centroidal state and foot kinematics from q, v) and the
-        reference's IK module for xs/us; neither is part of the hot path nor available in this image."""
+    def centroidal_inputs(self, q, v, v_des, w_des):
+        """What abstract_cyclic_gen.py:633-643 + create_cnt_plan (:159-177) + create_costs (:532-560) read from (q, v)
+        through pinocchio: the centroidal state, the feet, the yaw, the body-frame velocity goal, the orientation-correction
+        momentum and the yaw-rotated hip offsets -- the inputs of the batched problem builder.  q is modified in place
+        like the reference does (q[0:2] = 0).  Needs pinocchio and the robot wrapper passed to the constructor."""
         try:
-            import pinocchio as pin                                # noqa: F401
+            import pinocchio as pin
         except ImportError as e:
             raise ImportError("CyclicQuadrupedGaitGen.optimize(q, v, ...) needs pinocchio to compute the centroidal "
                               "state; use optimize_centroidal(...) with com / momentum / foot positions") from e
         if self.robot is None:
             raise ValueError("optimize(q, v, ...) needs the pinocchio robot wrapper passed to the constructor")
         rmodel, rdata = self.robot.model, self.robot.data
-        q = np.asarray(q, dtype=np.float64).copy()
         q[0:2] = 0                                                  # :633
+        ori_des = q[3:7] if w_des != 0 else [0, 0, 0, 1]            # :636-639
         R = pin.Quaternion(np.array(q[3:7])).toRotationMatrix()
         v_des = np.matmul(R, v_des)                                 # :642-643
-        pin.forwardKinematics(rmodel, rdata, q, v)
+        pin.forwardKinematics(rmodel, rdata, q, v)                  # :161-166
         pin.updateFramePlacements(rmodel, rdata)
-        com = pin.centerOfMass(rmodel, rdata, q, v)
-        pin.computeCentroidalMomentum(rmodel, rdata)
+        com = np.array(pin.centerOfMass(rmodel, rdata, q, v))
+        pin.computeCentroidalMomentum(rmodel, rdata)                # :536-540
         hg = np.array(rdata.hg)
-        foot = np.stack([rdata.oMf[rmodel.getFrameId(nm)].translation for nm in self.eff_names])
-        yaw = pin.rpy.matrixToRpy(R)[2]
-        com_int, mom_int, f_int = self.optimize_centroidal(com, hg[0:3] / self.m, hg[3:6], foot, t, v_des, w_des, yaw=yaw)
+        foot = np.stack([np.array(rdata.oMf[rmodel.getFrameId(nm)].translation) for nm in self.eff_names])
+        yaw = pin.rpy.matrixToRpy(R)[2]                             # :172-177
+        R_yaw = pin.rpy.rpyToMatrix(np.array([0.0, 0.0, yaw]))
+        hip_xy = np.array([np.matmul(R_yaw, np.asarray(self.rc.hip_offsets)[j])[0:2] for j in range(self.n_eff)])   # :279,347
+        # the desired orientation keeps only its yaw (:547-549); the momentum that corrects the difference (:616-627)
+        yaw_des = pin.rpy.matrixToRpy(pin.Quaternion(np.array(ori_des, dtype=np.float64)).toRotationMatrix())[2]
+        des_quat = pin.Quaternion(pin.rpy.rpyToMatrix(np.array([0.0, 0.0, yaw_des])))
+        amom_des = pin.log3((des_quat * (pin.Quaternion(np.array(q[3:7])).inverse())).toRotationMatrix())
+        return dict(com=com, vcom=hg[0:3] / self.m, amom=hg[3:6], foot_pos=foot, v_des=v_des, yaw=yaw,
+                    amom_des=np.asarray(amom_des, dtype=np.float64), hip_xy=hip_xy)
+
+    def optimize(self, q, v, t, v_des, w_des, X_wm=None, F_wm=None, P_wm=None, noise_std=None, mcts_x_y_cnt_loc=None,
+                 v_feet_des=None, ee_pos=None, z_height=None):
+        """abstract_cyclic_gen.py:629-698 without the IK: (q, v) -> centroidal problem (centroidal_inputs) -> solve ->
+        1 kHz interpolation.  Returns (None, None, f_int): xs_int / us_int come from the reference's IK module, which is
+        out of scope; com_int / mom_int / f_int are kept on the object like the reference does."""
+        c = self.centroidal_inputs(q, v, v_des, w_des)
+        com_int, mom_int, f_int = self.optimize_centroidal(c["com"], c["vcom"], c["amom"], c["foot_pos"], t, c["v_des"],
+                                                           w_des, yaw=c["yaw"], amom_des=c["amom_des"], hip_xy=c["hip_xy"])
         self.com_int, self.mom_int, self.f_int = com_int, mom_int, f_int
         return None, None, f_int                                    # xs_int, us_int come from the IK (out of scope)
 

@@ -92,6 +92,9 @@ def main():
                     cnt_plan=np.array(mp.cnt_plan), dt=np.array(mp.dt), X_nom=mp.X_nom, X_ter=mp.X_ter, W_X=mp.W_X,
                     W_X_ter=mp.W_X_ter, W_F=mp.W_F, bounds=mp.bounds, rho=mp.rho, x_init=gg.X_init.copy())
         out[f"{name}/gait"] = gait
+        # what SoloMpcGaitGen.optimize itself is called with (no further random draws): tests run the shim's
+        # optimize(q, v, t, v_in, w_des) on a robot wrapper with the same injected kinematics
+        vals.update(q=q.copy(), qv=v.copy(), v_in=v_in, hg=hg)
         for k, v_ in vals.items():
             out[f"{name}/{k}"] = np.asarray(v_, dtype=np.float64)
         # ---- the same state through AbstractGaitGen (abstract_cyclic_gen1.py); no further random draws ----
@@ -126,6 +129,7 @@ def load(path=OUT):
     for name in z["names"]:
         d = {k: z[f"{name}/{k}"] for k in IN_KEYS + OUT_KEYS}
         d["gait"] = str(z[f"{name}/gait"])
+        d.update({k: z[f"{name}/{k}"] for k in ("q", "qv", "v_in", "hg")})
         d["gen1"] = {k: z[f"{name}/gen1/{k}"] for k in OUT_KEYS + ("hip_offsets", "hip_xy", "horizon")}
         cases.append((str(name), d))
     motions = {}

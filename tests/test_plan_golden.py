@@ -143,3 +143,65 @@ def test_device_builder_equals_abstract_gait_gen():
         assert np.array_equal(f["cnt_plan"][0], g1["cnt_plan"].reshape(-1)), (name, "cnt_plan")
         for k in ("dt", "x_init", "X_nom", "X_ter"):
             assert np.array_equal(f[k][0], g1[k]), (name, k)
+
+
+# ---- the generator's own entry point: SoloMpcGaitGen.optimize(q, v, t, v_des, w_des), abstract_cyclic_gen.py:629-698 ----
+def _fake_robot(d):
+    """The robot wrapper of oracle/pinshim (test infrastructure) with the case's kinematics injected: what pinocchio
+    would return for (q, v) is whatever the golden generator injected when the reference's python ran."""
+    import os
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "pinshim")
+    if shim not in sys.path:
+        sys.path.insert(0, shim)
+    import pinocchio as pin
+    robot = pin.FakeRobot(float(d["mass"]), nv=18)
+    robot.inject(com=d["com"], foot_pos=d["foot_pos"], hg=d["hg"])
+    return robot
+
+
+def _shim_gen(d):
+    from bunmpc_b200 import SoloMpcGaitGen
+    rc, prm = _robot_and_params(d)
+    gen = SoloMpcGaitGen(_fake_robot(d), "solo12.urdf", np.zeros(37), 0.05, None, robot_constants=rc)
+    gen.update_gait_params(prm, float(d["t"]), horizon=int(d["horizon"]))
+    return gen
+
+
+@pytest.mark.parametrize("name,d", CASES, ids=[c[0] for c in CASES])
+def test_optimize_q_v_front_end_equals_reference_python(name, d):
+    """(q, v) -> builder inputs (gait_gen.centroidal_inputs: origin reset, body-frame velocity goal, yaw, yaw-rotated hip
+    offsets, orientation-correction momentum) == what the reference's optimize / create_cnt_plan / create_costs derived
+    from the same (q, v) when the golden file was made.  Bit for bit."""
+    gen = _shim_gen(d)
+    q = d["q"].copy()
+    q[0:2] = [0.3, -0.2]                      # optimize resets the origin itself (:633)
+    c = gen.centroidal_inputs(q, d["qv"].copy(), d["v_in"].copy(), float(d["w_des"]))
+    assert q[0] == 0 and q[1] == 0
+    for k in ("com", "vcom", "amom", "foot_pos", "v_des", "yaw", "amom_des", "hip_xy"):
+        assert np.array_equal(np.asarray(c[k]), d[k]), k
+
+
+@pytest.mark.gpu
+def test_optimize_q_v_equals_reference_plan_and_oracle_solution(oracle):
+    """SoloMpcGaitGen.optimize(q, v, ...) end to end on the GPU: the problem it hands to the solver is the reference
+    python's, bit for bit; the solution is the oracle's for that problem; f_int / com_int / mom_int are the 1 kHz
+    interpolation of :677-692."""
+    for name, d in CASES[:12]:
+        gen = _shim_gen(d)
+        xs, us, f_int = gen.optimize(d["q"].copy(), d["qv"].copy(), float(d["t"]), d["v_in"].copy(), float(d["w_des"]))
+        assert xs is None and us is None                     # the IK is out of scope
+        batch, sol = gen.last
+        n = int(d["horizon"])
+        assert batch.n_col == n
+        for k in ("cnt_plan", "dt", "x_init", "X_nom", "X_ter"):
+            assert np.array_equal(getattr(batch, k)[0], d[k]), (name, k)
+        assert np.array_equal(np.broadcast_to(batch.bounds, (1, n, 6))[0], d["bounds"])
+        ref = oracle.solve(batch)
+        for k in ("X", "F", "iters", "status"):
+            assert np.array_equal(getattr(sol, k), ref[k].reshape(getattr(sol, k).shape), equal_nan=True), (name, k)
+        F = sol.F[0].reshape(n, 12)
+        dt = batch.dt[0]
+        want = np.vstack([np.linspace(F[i], F[i + 1], int(dt[i] / 0.001)) for i in range(gen.size)])
+        assert np.array_equal(f_int, want) and np.array_equal(gen.f_int, want)
+        assert gen.com_int.shape == (want.shape[0], 3) and gen.mom_int.shape == (want.shape[0], 6)
