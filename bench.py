@@ -303,10 +303,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="instances per GPU per step")
     ap.add_argument("--arith", default="strict", choices=["strict", "fma", "mixed"])
-    ap.add_argument("--split", default="fixed", choices=["fixed", "balanced"],
+    ap.add_argument("--split", default="fixed", choices=["fixed", "balanced", "fused"],
                     help="multi-GPU only: 'fixed' = instance i -> rank i mod G (ShardedSolver, the default: measured equal or "
                          "faster at 2 and 8 GPUs, DESIGN.md section 7), 'balanced' = one fresh-instance counter for all GPUs "
-                         "over NVLink peer memory (bunmpc_b200.dist.BalancedSolver)")
+                         "over NVLink peer memory (bunmpc_b200.dist.BalancedSolver), 'fused' = the same counter and the solve "
+                         "kernel stores every finished instance into the result rows of ALL GPUs (no collective on the results)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     args = ap.parse_args()
@@ -336,9 +337,10 @@ def main():
     # i mod world.  Weak scaling: B instances per GPU at every N.
     global_batch = synthetic.config(1, B=world * B, seed=0)
     balanced = None
-    if world > 1 and args.split == "balanced":
+    if world > 1 and args.split in ("balanced", "fused"):
         try:
-            balanced = BalancedSolver(global_batch.n_col, global_batch.n_eff, job_batch=world * B, device=local_rank)
+            balanced = BalancedSolver(global_batch.n_col, global_batch.n_eff, job_batch=world * B, device=local_rank,
+                                      exchange="peer" if args.split == "fused" else "allreduce")
         except RuntimeError as exc:        # every rank raises or none does (the ranks agree inside the constructor)
             if rank == 0:
                 print(f"bench: balanced split unavailable ({exc}); using the fixed split", file=sys.stderr)
@@ -533,11 +535,13 @@ def main():
                    "arith": args.arith, "l2": "flushed between steps (256 MiB write)",
                    "sharding": (f"one global batch of {world * B} instances resident on every GPU; the CTAs of all GPUs pull "
                                 "instance ids from ONE counter in rank 0's HBM (system-scope atomics over NVLink peer "
-                                "memory, CUDA IPC); per step: NCCL all_reduce of the zero-filled result rows (exact), "
+                                "memory, CUDA IPC); per step: " + ("the solve kernel stores each finished instance into the "
+                                "result rows of every GPU (peer stores over NVLink), two one-word all_reduce as barriers, "
+                                if args.split == "fused" else "NCCL all_reduce of the zero-filled result rows (exact), ") +
                                 "all_reduce of 17 posterior statistics (bunmpc_b200.dist.BalancedSolver)"
                                 if balanced is not None else
                                 f"one global batch of {world * B} instances, instance i -> rank i mod {world}" + ("; per step: NCCL all_gather of F and X, all_reduce of 17 posterior statistics (bunmpc_b200.dist.ShardedSolver)" if world > 1 else "")),
-                   **({"split": "balanced" if balanced is not None else "fixed"} if world > 1 else {}),
+                   **({"split": args.split if balanced is not None else "fixed"} if world > 1 else {}),
                    "kernel": info},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

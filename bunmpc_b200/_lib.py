@@ -74,7 +74,8 @@ EXPORTS = ("bunmpc_version", "bunmpc_last_error", "bunmpc_default_params", "bunm
            "bunmpc_launch_count", "bunmpc_kernel_info", "bunmpc_expand_device", "bunmpc_solve_expanded_device",
            "bunmpc_solve_compact_device", "bunmpc_build_problem_device", "bunmpc_build_acyclic_device", "bunmpc_solve_compact_host", "bunmpc_solve_expanded_host",
            "bunmpc_goal_stats_device", "bunmpc_job_counter_create", "bunmpc_job_counter_open", "bunmpc_job_counter_release",
-           "bunmpc_set_job_counter", "bunmpc_centroidal_mats_host", "bunmpc_measure_fp64_peak", "bunmpc_selftest_division", "bunmpc_host_alloc", "bunmpc_host_free")
+           "bunmpc_set_job_counter", "bunmpc_peer_buffer_create", "bunmpc_peer_buffer_open", "bunmpc_peer_buffer_release",
+           "bunmpc_set_peer_results", "bunmpc_centroidal_mats_host", "bunmpc_measure_fp64_peak", "bunmpc_selftest_division", "bunmpc_host_alloc", "bunmpc_host_free")
 
 _lib = None
 
@@ -117,6 +118,10 @@ def lib():
     L.bunmpc_job_counter_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
     L.bunmpc_job_counter_release.argtypes = [C.c_void_p, C.c_int]
     L.bunmpc_set_job_counter.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.bunmpc_peer_buffer_create.argtypes = [C.c_int, C.c_ulonglong, C.POINTER(C.c_void_p), C.c_char_p]
+    L.bunmpc_peer_buffer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.bunmpc_peer_buffer_release.argtypes = [C.c_void_p, C.c_int]
+    L.bunmpc_set_peer_results.argtypes = [C.c_void_p, C.c_int, C.POINTER(Solution)]
     L.bunmpc_centroidal_mats_host.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 9
     L.bunmpc_measure_fp64_peak.argtypes = [C.c_void_p, dp]
     L.bunmpc_selftest_division.argtypes = [C.c_void_p, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]

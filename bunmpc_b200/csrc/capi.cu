@@ -32,6 +32,7 @@ struct bunmpc_solver {
     cudaStream_t stream = nullptr;
     unsigned int *job_counters = nullptr;   // [2] fresh-instance counters of a multi-GPU job (bunmpc_set_job_counter), device or peer memory
     int job_owner = 0; unsigned long long job_step = 0;
+    PeerOut *peers = nullptr; int n_peers = 0;   // [kMaxPeers] result rows of the job's other GPUs (bunmpc_set_peer_results)
     unsigned int *work_counter = nullptr;   // [2 + 2 kParkQueues]: next fresh instance, finished instances, tail / head of each queue of parked instances
     int *queue = nullptr; double *sl_d = nullptr; int *sl_i = nullptr; long long *sl_c = nullptr;   // time slicing
     double *coef = nullptr;          // device, [coef_len]
@@ -62,6 +63,7 @@ static void free_solver(bunmpc_solver *s)
 {
     if (!s) return;
     cudaFree(s->queue); cudaFree(s->sl_d); cudaFree(s->sl_i); cudaFree(s->sl_c);
+    cudaFree(s->peers);
     cudaFree(s->work_counter); cudaFree(s->coef); cudaFree(s->st_in); cudaFree(s->ex);
     cudaFree(s->out_d); cudaFree(s->out_i); cudaFree(s->out_c); cudaFree(s->mats); cudaFree(s->hist);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -134,6 +136,52 @@ int bunmpc_set_job_counter(bunmpc_solver *s, void *counters, int owner)
 {
     if (!s) return fail(BUNMPC_ERR_ARG, "set_job_counter: null solver");
     s->job_counters = (unsigned int *)counters; s->job_owner = owner ? 1 : 0; s->job_step = 0;
+    return BUNMPC_OK;
+}
+
+// ---- result buffers that the other GPUs of a job can store into: a device allocation exported as a CUDA IPC handle ----
+int bunmpc_peer_buffer_create(int device, unsigned long long bytes, void **ptr, unsigned char handle[64])
+{
+    if (!ptr || !handle || bytes == 0) return fail(BUNMPC_ERR_ARG, "peer_buffer_create: bad argument");
+    CK(cudaSetDevice(device));
+    void *p = nullptr;
+    CK(cudaMalloc(&p, (size_t)bytes));
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(BUNMPC_ERR_CUDA, std::string("peer_buffer_create: ") + cudaGetErrorString(e)); }
+    memcpy(handle, &h, 64);
+    *ptr = p;
+    return BUNMPC_OK;
+}
+
+int bunmpc_peer_buffer_open(int device, const unsigned char handle[64], void **ptr)
+{
+    return bunmpc_job_counter_open(device, handle, ptr);
+}
+
+int bunmpc_peer_buffer_release(void *ptr, int owner)
+{
+    return bunmpc_job_counter_release(ptr, owner);
+}
+
+int bunmpc_set_peer_results(bunmpc_solver *s, int n_peers, const bunmpc_solution *peers)
+{
+    if (!s || n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !peers))
+        return fail(BUNMPC_ERR_ARG, "set_peer_results: bad argument");
+    CK(cudaSetDevice(s->device));
+    PeerOut h[kMaxPeers];
+    for (int g = 0; g < n_peers; ++g) {
+        const bunmpc_solution &q = peers[g];
+        if (!q.X || !q.F || !q.L || !q.viol || !q.iters || !q.status)
+            return fail(BUNMPC_ERR_ARG, "set_peer_results: X, F, L, viol, iters and status are required for every peer");
+        h[g] = PeerOut{q.X, q.F, q.L, q.viol, q.iters, q.status};
+    }
+    if (n_peers > 0) {
+        if (!s->peers) CK(cudaMalloc(&s->peers, sizeof(PeerOut) * kMaxPeers));
+        CK(cudaMemcpy(s->peers, h, sizeof(PeerOut) * n_peers, cudaMemcpyHostToDevice));
+    }
+    s->n_peers = n_peers;
     return BUNMPC_OK;
 }
 
@@ -335,6 +383,7 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     a.long_inner = 2500.f;      // scheduling heuristic (kernels.cuh, parking code); never changes a result
     if (const char *ev = getenv("BUNMPC_LONG_INNER")) a.long_inner = (float)atof(ev);
     CK(cudaMemsetAsync(s->work_counter, 0, kWorkCounters * sizeof(unsigned int), st));
+    a.peers = s->peers; a.n_peers = s->n_peers;
     a.job_counter = nullptr;
     if (s->job_counters) {
         // solve k of the job pulls from counter k & 1; the owner clears the other one for solve k + 1.  Between two solves

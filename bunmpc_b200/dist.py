@@ -171,7 +171,12 @@ class BalancedSolver:
     # and the cycle counters stay with the rank that solved the row
     EXCHANGED = ("X", "F", "L", "viol", "iters", "status")
 
-    def __init__(self, n_col: int, n_eff: int = 4, job_batch: int = 8192, device: int = 0):
+    def __init__(self, n_col: int, n_eff: int = 4, job_batch: int = 8192, device: int = 0, exchange: str = "allreduce"):
+        """exchange = "allreduce": NCCL all_reduce of the zero-filled result rows after the solve (above);
+        exchange = "peer": the fused exchange of include/bunmpc.h (bunmpc_set_peer_results) -- every rank's result rows
+        live in a CUDA-IPC buffer that the other ranks map, and the solve kernel's epilogue stores a finished instance
+        into the rows of all GPUs; a one-word all_reduce before and after the solve are the only collectives left
+        (nobody still reads the previous rows / every rank's kernel has finished)."""
         import ctypes as C
 
         import torch
@@ -183,6 +188,10 @@ class BalancedSolver:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         if job_batch % (2 * self.world):
             raise ValueError("job_batch must be a multiple of 2 * world (int32 result fields are exchanged as int64 words)")
+        if exchange not in ("allreduce", "peer"):
+            raise ValueError("exchange must be 'allreduce' or 'peer'")
+        self.exchange = exchange if self.world > 1 else "allreduce"
+        self._flat_ptr, self._peer_ptrs = C.c_void_p(), []
         self.device, self.job_batch, self.shard = device, job_batch, job_batch // self.world
         self.solver = BatchSolver(n_col, n_eff, max_batch=job_batch, device=device)
         self.stats = torch.zeros(17, dtype=torch.float64, device=torch.device("cuda", device))
@@ -209,6 +218,26 @@ class BalancedSolver:
 
     def close(self):
         from . import _lib
+        if getattr(self, "_peer_ptrs", None) or (getattr(self, "_flat_ptr", None) is not None and self._flat_ptr.value):
+            import torch
+            torch.cuda.synchronize(self.device)
+            if getattr(self, "solver", None) is not None and self.solver._h.value:
+                _lib.lib().bunmpc_set_peer_results(self.solver._h, 0, None)
+            for p in self._peer_ptrs:
+                _lib.lib().bunmpc_peer_buffer_release(p, 0)
+            self._peer_ptrs = []
+            self.flat = None
+            if self.dev is not None:
+                self.dev.out = {}
+            if self._flat_ptr.value:
+                try:        # the peers close their mappings of this buffer before it is freed (close() is collective)
+                    import torch.distributed as dist
+                    if dist.is_initialized() and self.world > 1:
+                        dist.barrier()
+                except Exception:
+                    pass
+                _lib.lib().bunmpc_peer_buffer_release(self._flat_ptr, 1)
+                self._flat_ptr.value = None
         if getattr(self, "_counters", None) is not None and self._counters.value:
             if getattr(self, "solver", None) is not None and self.solver._h.value:
                 _lib.lib().bunmpc_set_job_counter(self.solver._h, None, 0)
@@ -237,15 +266,73 @@ class BalancedSolver:
                       P=((B, self.solver.nx), torch.float64), cycles=((B,), torch.int64))
         words = {k: int(np.prod(sh)) * (1 if dt != torch.int32 else 0) + (int(np.prod(sh)) // 2 if dt == torch.int32 else 0)
                  for k, (sh, dt) in shapes.items()}
-        self.flat = torch.zeros(sum(words.values()), dtype=torch.int64, device=dev)
-        off = 0
+        n_words = sum(words.values())
+        if self.exchange == "peer":
+            self.flat = self._peer_flat(n_words)
+        else:
+            self.flat = torch.zeros(n_words, dtype=torch.int64, device=dev)
+        off, offs = 0, {}
         for k in self.EXCHANGED + ("P", "cycles"):
             sh, dt = shapes[k]
             self.dev.out[k] = self.flat[off:off + words[k]].view(dt).view(sh)
+            offs[k] = 8 * off
             off += words[k]
             if k == self.EXCHANGED[-1]:
                 self.n_exchanged = off
+        if self.exchange == "peer":
+            self._register_peers(offs)
+            self._word = torch.zeros(1, dtype=torch.int32, device=dev)
         return self.dev
+
+    def _peer_flat(self, n_words: int):
+        """The flat result buffer as a CUDA-IPC allocation of the library, wrapped as a torch tensor; the other ranks'
+        buffers mapped into this process."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        L, buf = _lib.lib(), C.create_string_buffer(64)
+        ok = int(L.bunmpc_peer_buffer_create(self.device, 8 * n_words, C.byref(self._flat_ptr), buf) == _lib.OK)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, buf.raw if ok else None)
+        if ok and all(h is not None for h in handles):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    continue
+                p = C.c_void_p()
+                if L.bunmpc_peer_buffer_open(self.device, h, C.byref(p)) != _lib.OK:
+                    ok = 0
+                    break
+                self._peer_ptrs.append(p)
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", self.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            err = (L.bunmpc_last_error() or b"").decode()
+            self.close()
+            raise RuntimeError("BalancedSolver: the result rows could not be mapped between the ranks (CUDA IPC): " + err)
+
+        class _Raw:       # torch.as_tensor reads __cuda_array_interface__
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (int(self._flat_ptr.value), False),
+                                        "version": 2}
+        self._raw = raw
+        return torch.as_tensor(raw, device=torch.device("cuda", self.device))
+
+    def _register_peers(self, offs: dict):
+        import ctypes as C
+
+        from . import _lib
+        arr = (_lib.Solution * len(self._peer_ptrs))()
+        for g, p in enumerate(self._peer_ptrs):
+            base = int(p.value)
+            arr[g] = _lib.Solution(base + offs["X"], base + offs["F"], None, base + offs["L"], base + offs["iters"],
+                                   base + offs["viol"], base + offs["status"], None, None)
+        _lib.check(_lib.lib().bunmpc_set_peer_results(self.solver._h, len(self._peer_ptrs), arr), "bunmpc_set_peer_results")
 
     def load_own_rows(self, pinned: dict):
         """e2e: this rank's instances arrive from ITS host (pinned tensors of its shard, [shard, w] per per-instance
@@ -268,10 +355,16 @@ class BalancedSolver:
         import torch.distributed as dist
 
         from . import _lib
-        self.flat.zero_()
-        out = self.solver.solve_resident(self.dev, params=params, arith=arith)
-        if self.world > 1:
-            dist.all_reduce(self.flat[:self.n_exchanged], op=dist.ReduceOp.SUM)
+        if self.exchange == "peer":
+            dist.all_reduce(self._word)                    # no rank still reads the rows of the previous step
+            self.flat[self.n_exchanged:].zero_()           # P and the cycle counters: set on the rank that solves the row
+            out = self.solver.solve_resident(self.dev, params=params, arith=arith)   # stores every row on every GPU
+            dist.all_reduce(self._word)                    # every rank's kernel has finished: all rows are here
+        else:
+            self.flat.zero_()
+            out = self.solver.solve_resident(self.dev, params=params, arith=arith)
+            if self.world > 1:
+                dist.all_reduce(self.flat[:self.n_exchanged], op=dist.ReduceOp.SUM)
         if stats:
             g, e = self.dev.fields["X_ter"], out["viol"]
             o = self.rank * self.shard

@@ -217,6 +217,20 @@ int bunmpc_job_counter_open(int device, const unsigned char ipc_handle[64], void
 int bunmpc_job_counter_release(void *counters, int owner);
 int bunmpc_set_job_counter(bunmpc_solver *s, void *counters, int owner);
 
+/* Fused exchange: result buffers that the other GPUs of the job store into.  Every rank allocates its result rows with
+ * bunmpc_peer_buffer_create (device memory + 64-byte CUDA IPC handle), sends the handle to the other ranks' processes,
+ * opens theirs with bunmpc_peer_buffer_open and registers, per peer, where that peer's X, F, L, viol, iters and status
+ * rows live (bunmpc_set_peer_results; the other members of bunmpc_solution are ignored).  From then on the CTA that
+ * finishes instance b stores row b into its own `out` buffers AND into every registered peer's (plain stores to peer
+ * memory over NVLink / NVSwitch from the solve kernel's epilogue): when every rank's solve has finished -- any
+ * collective or barrier of the job after the solve tells -- every rank holds every row, and no collective moves results.
+ * A rank must not start the next solve of the job while a peer still reads the rows of this one (one more barrier).
+ * n_peers == 0 switches the stores off.  At most 15 peers. */
+int bunmpc_peer_buffer_create(int device, unsigned long long bytes, void **ptr, unsigned char ipc_handle[64]);
+int bunmpc_peer_buffer_open(int device, const unsigned char ipc_handle[64], void **ptr);
+int bunmpc_peer_buffer_release(void *ptr, int owner);
+int bunmpc_set_peer_results(bunmpc_solver *s, int n_peers, const bunmpc_solution *peers);
+
 /* Sufficient statistics of the Bayesian goal update over one rank's shard (the reference's grid posterior with a Gaussian
  * likelihood centred at the sampled goal, locosafedagger_modified.py:357-402): goals [B][3] (batch stride in elements,
  * e.g. the desired velocity X_ter + 3 with stride 9), errors [B] (NaN counts as 0) -> out17 = [N, sum g (3),

@@ -80,7 +80,7 @@ def test_sharded_step_single_gpu(oracle):
 BJ = 600          # more instances than resident CTAs per GPU, so instances are parked and resumed as well
 
 
-def _balanced_worker(rank, world, port, q):
+def _balanced_worker(rank, world, port, q, exchange="allreduce"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -91,7 +91,7 @@ def _balanced_worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     batch = synthetic.perturbed(BJ, seed=6)
-    bs = BalancedSolver(batch.n_col, batch.n_eff, job_batch=BJ, device=rank)
+    bs = BalancedSolver(batch.n_col, batch.n_eff, job_batch=BJ, device=rank, exchange=exchange)
     bs.upload_global(batch)
     prm = SolverParams(max_outer=12, slice_outer=3)
     pulled = []
@@ -106,9 +106,12 @@ def _balanced_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_balanced_step_two_gpus_nccl(oracle):
+@pytest.mark.parametrize("exchange", ["allreduce", "peer"])
+def test_balanced_step_two_gpus_nccl(oracle, exchange):
     """Two GPUs pull the instances of one job from one counter (NVLink atomics on CUDA-IPC peer memory); every rank ends
-    with every result, bit for bit the oracle's, whichever GPU solved it; together they solved each instance once."""
+    with every result, bit for bit the oracle's, whichever GPU solved it; together they solved each instance once.
+    exchange = "peer": the solve kernel itself stores each finished instance into both GPUs' result rows (fused
+    exchange, bunmpc_set_peer_results) instead of an all_reduce of the rows afterwards."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -118,7 +121,8 @@ def test_balanced_step_two_gpus_nccl(oracle):
     world, port = 2, 31700 + os.getpid() % 2000
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_balanced_worker, args=(r, world, port, q)) for r in range(world)]
+    port += 7 * (exchange == "peer")
+    procs = [ctx.Process(target=_balanced_worker, args=(r, world, port, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
