@@ -250,5 +250,16 @@ class GoalPosterior:
         return self.p
 
     def update(self, observed_goal):
-        """One observation, exactly locosafedagger_modified.py:357-402."""
+        """One observation, locosafedagger_modified.py:357-402 as its signature and docstring describe it: the Gaussian is
+        centred at the observed goal (vx, vy, w)."""
         return self.update_batch(np.asarray(observed_goal, dtype=np.float64)[None])
+
+    def update_as_called(self, v_des, w_des, error):
+        """One observation the way the reference's ONLY call site passes it (locosafedagger_modified.py:611):
+        `compute_likelihood(vx_vals, vy_vals, w_vals, v_des[0], v_des[1], w_des, self.errors[-1], sigma=0.1)` binds
+        observed_goal = v_des[0] (unused), vx_obs = v_des[1], vy_obs = w_des, w_obs = error -- the arguments are shifted by
+        one against the signature at :357, so the Gaussian the reference actually multiplies in is centred at
+        (v_des[1], w_des, error).  A reference bug; `update` is the documented behaviour, this one the
+        executed behaviour, and a caller reproducing the reference's runs needs this one."""
+        v = np.asarray(v_des, dtype=np.float64).reshape(-1)
+        return self.update_batch(np.array([[v[1], float(w_des), float(error)]], dtype=np.float64))

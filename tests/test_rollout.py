@@ -102,6 +102,27 @@ def test_goal_posterior_matches_single_updates():
     assert abs(np.average(gp.axes[0], weights=both.p.sum((1, 2))) - s[:, 0].mean()) < 0.02
 
 
+def test_goal_posterior_update_as_the_reference_calls_it():
+    """locosafedagger_modified.py:611 passes (v_des[0], v_des[1], w_des, error) into (observed_goal, vx_obs, vy_obs, w_obs):
+    the triple loop of :374-384 with those bindings, restated here on a small grid, is what update_as_called multiplies
+    in; update() is the documented (unshifted) behaviour and differs."""
+    from bunmpc_b200.rollout import GoalPosterior
+    gp, doc = GoalPosterior(n=9), GoalPosterior(n=9)
+    v_des, w_des, error, sigma = np.array([0.22, -0.04, 0.0]), 0.06, 0.031, 0.1
+    vx_obs, vy_obs, w_obs = v_des[1], w_des, error                  # the call's bindings
+    lik = np.zeros((9, 9, 9))
+    for i, vx in enumerate(gp.axes[0]):
+        for j, vy in enumerate(gp.axes[1]):
+            for k, w in enumerate(gp.axes[2]):
+                d = np.array([vx - vx_obs, vy - vy_obs, w - w_obs])
+                lik[i, j, k] = np.exp(-np.sum(d ** 2) / (2 * sigma ** 2))
+    lik /= lik.sum()
+    post = np.full((9, 9, 9), 1.0 / 9 ** 3) * lik
+    post /= post.sum()
+    assert np.allclose(gp.update_as_called(v_des, w_des, error), post, rtol=1e-12)
+    assert not np.allclose(doc.update([v_des[0], v_des[1], w_des]), post, rtol=1e-3)
+
+
 @pytest.mark.gpu
 def test_lockstep_rollouts_gpu_equals_oracle(oracle):
     import torch
