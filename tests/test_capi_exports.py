@@ -42,3 +42,18 @@ def test_product_code_never_touches_the_oracle():
                 assert not re.search(r'#\s*include\s*[<"][^>"]*oracle', txt), f
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f
                 assert "libbicon_oracle" not in txt and "dlopen" not in txt, f
+
+
+def test_multi_gpu_entry_points_reject_bad_arguments_without_gpu():
+    """The argument checks of the job-counter / peer-result entry points come before any CUDA call."""
+    from bunmpc_b200 import _lib
+    L = _lib.lib()
+    p, buf = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+    assert L.bunmpc_set_job_counter(None, None, 0) == _lib.ERR_ARG
+    assert L.bunmpc_set_peer_results(None, 0, None) == _lib.ERR_ARG
+    assert L.bunmpc_job_counter_create(0, None, buf) == _lib.ERR_ARG
+    assert L.bunmpc_job_counter_open(0, None, ctypes.byref(p)) == _lib.ERR_ARG
+    assert L.bunmpc_peer_buffer_create(0, 0, ctypes.byref(p), buf) == _lib.ERR_ARG      # zero bytes
+    assert L.bunmpc_peer_buffer_open(0, buf.raw, None) == _lib.ERR_ARG
+    assert L.bunmpc_peer_buffer_release(None, 1) == _lib.OK and L.bunmpc_job_counter_release(None, 0) == _lib.OK
+    assert b"null" in L.bunmpc_last_error() or b"bad" in L.bunmpc_last_error()
