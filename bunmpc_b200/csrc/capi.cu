@@ -380,7 +380,7 @@ int bunmpc_solve_expanded_device(bunmpc_solver *s, const bunmpc_expanded_problem
     }
     a.slice_outer = slice; a.queue_cap = kQueuePerInstance * a.B;
     a.queue = s->queue; a.sl_d = s->sl_d; a.sl_i = s->sl_i; a.sl_c = s->sl_c;
-    a.long_inner = 2500.f;      // scheduling heuristic (kernels.cuh, parking code); never changes a result
+    a.long_inner = 1000.f;      // scheduling heuristic (kernels.cuh, parking code; profiles/r02_sched_probe3.txt); never changes a result
     if (const char *ev = getenv("BUNMPC_LONG_INNER")) a.long_inner = (float)atof(ev);
     CK(cudaMemsetAsync(s->work_counter, 0, kWorkCounters * sizeof(unsigned int), st));
     a.peers = s->peers; a.n_peers = s->n_peers;

@@ -55,7 +55,7 @@ typedef struct {
                          * CTAs, else off), < 0 = off.  Parked instances are resumed longest predicted remainder first
                          * (eight queues; the estimate extrapolates the decay of the dynamics violation over the slice);
                          * environment BUNMPC_LONG_INNER = the scale of the predicted remaining inner iterations that
-                         * separate the queues (x 0.2 .. x 3.6; default 2500) -- a tuning knob, it never changes a result */
+                         * separate the queues (x 0.2 .. x 3.6; default 1000) -- a tuning knob, it never changes a result */
 } bunmpc_params;
 
 typedef struct {
