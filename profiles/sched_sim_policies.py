@@ -5,7 +5,9 @@ import sched_sim
 names = [f"g8192:{r}" for r in range(8)] + [f"g4096:{r}" for r in range(4)] + ["seed0", "seed5", "seed9"]
 data = {nm: sched_sim.per_outer_data(nm) for nm in names}
 
-def simulate(viol, itf, itx, slice_outer=8, long_inner=1000.0, first_slice=None, floor_until=0, floor_frac=0.5, n_cta=296):
+def simulate(viol, itf, itx, slice_outer=8, long_inner=1000.0, first_slice=None, floor_until=0, floor_frac=0.5, n_cta=296,
+             end_slices=None):
+    """end_slices = ((unfinished instances <= a, slice), ...): shorter slices once fewer instances than that are unfinished"""
     B = viol.shape[0]
     outer_n = (~np.isnan(viol)).sum(1)
     cost = (17.2e3 + 1333.0 * itf + 853.0 * itx) * (1394.0 / 1120.0) / 1.965e6
@@ -25,6 +27,8 @@ def simulate(viol, itf, itx, slice_outer=8, long_inner=1000.0, first_slice=None,
         if i < 0: return False
         o0 = done[i]
         sl = first_slice if (o0 == 0 and first_slice) else slice_outer
+        for a, s_ in (end_slices or ()):
+            if B - finished <= a: sl = min(sl, s_)
         o1 = min(o0 + sl, outer_n[i])
         last_k[i] = o1 - o0
         done[i] = o1
@@ -63,3 +67,8 @@ for fu, ff in ((16, 0.5), (16, 0.8), (24, 0.5), (24, 0.8), (32, 0.6)):
     print(f"floor until {fu} frac {ff}        ", ev(floor_until=fu, floor_frac=ff), flush=True)
 for fs, fu, ff in ((16, 24, 0.5), (16, 32, 0.6)):
     print(f"first {fs}, floor until {fu} frac {ff}", ev(first_slice=fs, floor_until=fu, floor_frac=ff), flush=True)
+# Shorter slices near the end, switched by the number of unfinished instances: no effect at all for thresholds up to 700 of
+# 1024 -- longest-remainder-first makes nearly everything end together, so "few unfinished" comes too late to matter; a
+# switch on the number of instances (1024, 2) is the short-slice case again (31 ms).
+for es in (((296, 4), (148, 2)), ((700, 4), (450, 1)), ((1024, 2),)):
+    print(f"end slices {str(es):40s}", ev(end_slices=es), flush=True)
