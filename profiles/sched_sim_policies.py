@@ -6,13 +6,13 @@ names = [f"g8192:{r}" for r in range(8)] + [f"g4096:{r}" for r in range(4)] + ["
 data = {nm: sched_sim.per_outer_data(nm) for nm in names}
 
 def simulate(viol, itf, itx, slice_outer=8, long_inner=1000.0, first_slice=None, floor_until=0, floor_frac=0.5, n_cta=296,
-             end_slices=None):
+             end_slices=None, halving=0):
     """end_slices = ((unfinished instances <= a, slice), ...): shorter slices once fewer instances than that are unfinished"""
     B = viol.shape[0]
     outer_n = (~np.isnan(viol)).sum(1)
     cost = (17.2e3 + 1333.0 * itf + 853.0 * itx) * (1394.0 / 1120.0) / 1.965e6
     c = np.array([0.2, 0.4, 0.8, 1.2, 1.8, 2.6, 3.6]) * long_inner
-    done = np.zeros(B, dtype=int); last_k = np.zeros(B, dtype=int)
+    done = np.zeros(B, dtype=int); last_k = np.zeros(B, dtype=int); rem_est = np.full(B, 1e9)
     queues = [[] for _ in range(8)]
     fresh = 0; finished = 0
     events = [(0.0, k, -1) for k in range(n_cta)]; heapq.heapify(events)
@@ -27,6 +27,8 @@ def simulate(viol, itf, itx, slice_outer=8, long_inner=1000.0, first_slice=None,
         if i < 0: return False
         o0 = done[i]
         sl = first_slice if (o0 == 0 and first_slice) else slice_outer
+        if halving and rem_est[i] < 2 * slice_outer:      # the slice shrinks with the estimated remainder: ceil(rem / halving), at least 1
+            sl = int(min(sl, max(1, np.ceil(rem_est[i] / halving))))
         for a, s_ in (end_slices or ()):
             if B - finished <= a: sl = min(sl, s_)
         o1 = min(o0 + sl, outer_n[i])
@@ -50,6 +52,7 @@ def simulate(viol, itf, itx, slice_outer=8, long_inner=1000.0, first_slice=None,
                     if rate > 1e-3: rem = min(rem, max(float((np.log(v1) - np.log(np.float32(1e-3))) / rate), 0.0))
                     per = (itf[i, o - k:o].sum() + itx[i, o - k:o].sum()) / k
                     if o <= floor_until: rem = max(rem, floor_frac * (100 - o))
+                    rem_est[i] = rem
                     q = int((rem * per > c).sum())
                 queues[q].append(i)
                 while idle and any(queues): take(t, idle.pop())
@@ -72,3 +75,6 @@ for fs, fu, ff in ((16, 24, 0.5), (16, 32, 0.6)):
 # switch on the number of instances (1024, 2) is the short-slice case again (31 ms).
 for es in (((296, 4), (148, 2)), ((700, 4), (450, 1)), ((1024, 2),)):
     print(f"end slices {str(es):40s}", ev(end_slices=es), flush=True)
+# The slice of a parked instance shrinks with its estimated remaining outer iterations (ceil(rem / h) once rem < 16):
+for h in (1.5, 2, 3):
+    print(f"slice = ceil(estimated remainder / {h})          ", ev(halving=h), flush=True)
